@@ -1,0 +1,13 @@
+"""harmonypy_b200 -- Blackwell-native engine for the Harmony inner loop.
+
+Public surface mirrors slowkow/harmonypy (harmonypy/__init__.py:1-4).
+"""
+__version__ = "0.1.0"
+
+
+def __getattr__(name):
+    # Lazy so that ``harmonypy_b200.synthetic`` can be used without touching CUDA.
+    if name in ("run_harmony", "Harmony"):
+        from . import harmony
+        return getattr(harmony, name)
+    raise AttributeError(name)

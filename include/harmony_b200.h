@@ -1,0 +1,116 @@
+/* harmony_b200.h -- C ABI of the Blackwell-native Harmony inner-loop engine.
+ *
+ * slowkow/harmonypy has no FFI: its boundary is the Python class ``Harmony``
+ * (harmonypy/harmony.py:218-569).  Each entry point below replaces one method (or the
+ * device-state part of one method) of that class; the Python host in
+ * harmonypy_b200/harmony.py keeps the reference's driver logic (harmonize / cluster loop /
+ * check_convergence, harmony.py:419-462, :515-533) verbatim in behaviour and calls these
+ * through ctypes.  INTEGRATION.md shows the stub a harmonypy maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; hmy_last_error(ctx) gives
+ *     the message (hmy_last_error(NULL) for failures of hmy_create itself);
+ *   - "host" pointers are ordinary (pageable or pinned) host memory owned by the caller;
+ *     the library owns every device allocation it makes;
+ *   - one context per GPU / per rank, not thread-safe; all work is enqueued on the stream
+ *     given to hmy_set_stream (default: the legacy default stream);
+ *   - matrices cross the boundary CELL-MAJOR: Z is n_cells x d (row stride d), R is
+ *     n_cells x K, codes are V x n_cells.  Y is K x d (one centroid per row).  O and E are
+ *     K x B (row stride B) like the reference's properties (harmony.py:313-321);
+ *   - B = sum(levels_per_var) one-hot rows in pd.get_dummies order (harmony.py:133):
+ *     covariate-major, level-minor.  Level codes are 0-based within their covariate.
+ */
+#ifndef HARMONY_B200_H
+#define HARMONY_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hmy_ctx hmy_ctx;
+
+/* Matrices readable with hmy_get (mirrors the NumPy properties, harmony.py:288-351). */
+enum hmy_matrix {
+    HMY_Z_CORR = 0, /* float  n_local x d   harmony.py:289-291 */
+    HMY_Z_COS  = 1, /* float  n_local x d   harmony.py:299-301 */
+    HMY_Z_ORIG = 2, /* float  n_local x d   harmony.py:294-296 */
+    HMY_R      = 3, /* float  n_local x K   harmony.py:304-306 */
+    HMY_Y      = 4, /* float  K x d (unit rows; transpose of harmony.py:309-311) */
+    HMY_O      = 5, /* double K x B         harmony.py:314-316 */
+    HMY_E      = 6, /* double K x B         harmony.py:319-321 */
+    HMY_W      = 7  /* float  B x K x d  ridge coefficients of the last hmy_ridge_correct */
+};
+
+/* Optional caller-supplied sum-all-reduce over ranks, called at the reduction points of the
+ * staged multi-GPU mode with a DEVICE pointer; must enqueue on (or synchronise with)
+ * `stream`.  dtype: 0 = float32, 1 = float64. */
+typedef int (*hmy_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int dtype, void* stream);
+
+const char* hmy_version(void);
+const char* hmy_last_error(const hmy_ctx* ctx);
+
+/* State owner.  Replaces Harmony.__init__ buffers + allocate_buffers (harmony.py:224-271,
+ * :357-364).  n_local cells live on this rank; they are cells [cell_offset, cell_offset +
+ * n_local) of the n_global cells the permutation indexes. */
+int hmy_create(hmy_ctx** out, int device, int64_t n_local, int64_t n_global, int64_t cell_offset,
+               int d, int K, int V, const int32_t* levels_per_var);
+void hmy_destroy(hmy_ctx* ctx);
+int hmy_set_stream(hmy_ctx* ctx, void* cuda_stream);
+
+/* Run parameters (harmony.py:242, :262-271): Pr_b[B], theta[B], sigma[K], lamb[B+1]
+ * (lamb[0] is the intercept's 0; ignored when lambda_estimation != 0, harmony.py:541-544). */
+int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* theta, const float* sigma,
+                   const float* lamb, int lambda_estimation, float alpha, float block_size);
+
+/* Upload this rank's cells: Z (n_local x d, fp32) and level codes (V x n_local, int32).
+ * Builds Z_cos (harmony.py:234-238).  Replaces the dense Phi / Phi_moe / batch_index
+ * construction (harmony.py:241-256) with integer codes. */
+int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* codes_host);
+
+/* Tail of init_cluster after sklearn (harmony.py:373-392): normalise the K x d centroids,
+ * R = softmax_k(-dist/sigma), O, E, and the three objective sums
+ * obj[0] = sum R*dist, obj[1] = sum sigma*R*log R, obj[2] = cross-entropy term
+ * (harmony.py:399-411; NOT yet multiplied by 2000/N). */
+int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0_host_Kxd, double obj[3]);
+
+/* One iteration of the loop body of cluster() (harmony.py:443-453): centroid update,
+ * cosine distances, blockwise update_R (harmony.py:464-513), objective.
+ * perm_host: the n_global-long randperm of harmony.py:471 (int64, host) or NULL to draw a
+ * device-side pseudo-random permutation from (seed, round counter). */
+int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double obj[3]);
+
+/* moe_correct_ridge (harmony.py:535-569): per-cluster ridge regression, Z_corr, Z_cos. */
+int hmy_ridge_correct(hmy_ctx* ctx);
+
+/* Property reads (harmony.py:288-351).  Cells come back in the caller's original order. */
+int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes);
+
+int hmy_synchronize(hmy_ctx* ctx);
+
+/* Options: "persistent" (0/1: one cooperative kernel per round vs one launch per block
+ * step), "seed" (device permutation seed), "tile_mode", ...  Unknown names fail. */
+int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value);
+
+/* Counters: "launches" (kernels launched by this library since creation), "rounds",
+ * "ridge_passes".  Timers (CUDA events on the context stream, milliseconds, cumulative):
+ * "ms_round", "ms_ridge".  Unknown names return -1. */
+int64_t hmy_counter(const hmy_ctx* ctx, const char* name);
+double hmy_timer_ms(hmy_ctx* ctx, const char* name);
+
+/* ---- multi-GPU (cells sharded over ranks) ---------------------- */
+
+/* Staged mode: the library calls `fn` wherever a small table must be summed over ranks. */
+int hmy_set_allreduce(hmy_ctx* ctx, hmy_allreduce_fn fn, void* user);
+
+/* Fused mode: ranks exchange the small tables inside the persistent round kernel through
+ * peer-mapped device memory.  Each rank exports a 64-byte handle of its exchange buffer;
+ * the caller all-gathers the handles (any transport) and hands every rank the full list. */
+int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B);
+int hmy_comm_attach(hmy_ctx* ctx, int rank, int world, const void* all_handles_world_x_64B);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HARMONY_B200_H */
