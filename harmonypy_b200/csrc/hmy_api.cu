@@ -1,0 +1,640 @@
+// C ABI of the Harmony engine (include/harmony_b200.h): context, uploads, stage launches.
+// Host-side orchestration only -- all arithmetic on cells happens in hmy_round.cuh /
+// hmy_ridge.cuh.  Built in-tree by __graft_entry__.build() with
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#define HMY_NONTEMPLATE_KERNELS 1
+#include "../../include/harmony_b200.h"
+#include "hmy_common.cuh"
+#include "hmy_round.cuh"
+#include "hmy_ridge.cuh"
+
+#define HMY_VERSION "harmony_b200 0.1.0 (sm_100a)"
+
+static thread_local std::string g_create_error;
+
+struct EventPair { cudaEvent_t a, b; };
+
+struct hmy_ctx {
+    HmyDev st{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::vector<int> levels, level_off;
+    int KPT = 0, JPW = 0;
+    int G = 0, sms = 0;
+    int smem_round = 0, smem_mom = 0, smem_apply = 0, smem_solve = 0;
+    int grid_ridge = 0;
+    bool persistent = true;
+    bool have_data = false, have_params = false, have_init = false;
+    unsigned long long seed = 0x243F6A8885A308D3ull;
+    unsigned int round_counter = 0, gen = 0;
+    float block_size = 0.05f;
+    // kernels bound to the (KPT, JPW) instantiation
+    const void* fn_round = nullptr; const void* fn_stage = nullptr;
+    const void* fn_mom = nullptr; const void* fn_apply = nullptr;
+    // device buffers
+    std::vector<void*> allocs;
+    float* Ybuf[2] = {nullptr, nullptr};
+    int ycur = 0;            // Ybuf[ycur] feeds the next stage
+    float* Ylast = nullptr;  // centroids the last finished round used (the reference's _Y)
+    unsigned char* zero_round = nullptr; size_t zero_round_bytes = 0;
+    unsigned char* zero_ridge = nullptr; size_t zero_ridge_bytes = 0;
+    long long* d_perm = nullptr;
+    float* d_tmp = nullptr; size_t tmp_bytes = 0;
+    double* h_obj = nullptr;     // pinned
+    // counters / timers
+    long long launches = 0, rounds = 0, ridge_passes = 0;
+    bool timing = true;
+    std::vector<EventPair> ev_round, ev_ridge;
+    double ms_round = 0.0, ms_ridge = 0.0;
+    // multi-GPU
+    hmy_allreduce_fn ar = nullptr; void* ar_user = nullptr;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char b_[512];                                                                          \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->err = b_;                                                                         \
+            return 1;                                                                              \
+        }                                                                                          \
+    } while (0)
+
+#define FAIL(msg) do { ctx->err = (msg); return 1; } while (0)
+
+template <class T>
+static int dev_alloc(hmy_ctx* ctx, T** p, size_t count) {
+    void* q = nullptr;
+    CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    ctx->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+// Each (KPT, JPW) instantiation of the streaming kernels lives in its own translation unit
+// (hmy_inst.cu, compiled once per pair so the build parallelises); it exports
+// hmy_bind_<KPT>_<JPW>(fns) filling {k_round, k_round_stage, k_ridge_moments, k_ridge_apply}.
+#define HMY_DECL_BIND(K_, J_) extern "C" void hmy_bind_##K_##_##J_(const void** fns);
+HMY_DECL_BIND(1, 4) HMY_DECL_BIND(1, 8) HMY_DECL_BIND(1, 16)
+HMY_DECL_BIND(2, 4) HMY_DECL_BIND(2, 8) HMY_DECL_BIND(2, 16)
+HMY_DECL_BIND(4, 4) HMY_DECL_BIND(4, 8) HMY_DECL_BIND(4, 16)
+HMY_DECL_BIND(8, 4) HMY_DECL_BIND(8, 8) HMY_DECL_BIND(8, 16)
+
+static bool bind_for(hmy_ctx* ctx) {
+    const void* f[4] = {nullptr, nullptr, nullptr, nullptr};
+    switch (ctx->KPT * 100 + ctx->JPW) {
+        case 104: hmy_bind_1_4(f); break;   case 108: hmy_bind_1_8(f); break;   case 116: hmy_bind_1_16(f); break;
+        case 204: hmy_bind_2_4(f); break;   case 208: hmy_bind_2_8(f); break;   case 216: hmy_bind_2_16(f); break;
+        case 404: hmy_bind_4_4(f); break;   case 408: hmy_bind_4_8(f); break;   case 416: hmy_bind_4_16(f); break;
+        case 804: hmy_bind_8_4(f); break;   case 808: hmy_bind_8_8(f); break;   case 816: hmy_bind_8_16(f); break;
+        default: return false;
+    }
+    ctx->fn_round = f[0]; ctx->fn_stage = f[1]; ctx->fn_mom = f[2]; ctx->fn_apply = f[3];
+    return true;
+}
+
+extern "C" const char* hmy_version(void) { return HMY_VERSION; }
+
+extern "C" const char* hmy_last_error(const hmy_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_global, int64_t cell_offset,
+                       int d, int K, int V, const int32_t* levels_per_var) {
+    HmyDev& st = ctx->st;
+    if (n_local < 1 || n_local > 2000000000LL) FAIL("n_local out of range (1 .. 2e9 cells per rank)");
+    if (n_global < n_local || cell_offset < 0 || cell_offset + n_local > n_global) FAIL("cell range outside n_global");
+    if (d < 1 || d > 128) FAIL("d must be in 1..128");
+    if (K < 2 || K > 256) FAIL("K (nclust) must be in 2..256");
+    if (V < 1 || V > HMY_MAX_V) FAIL("number of batch covariates must be in 1..8");
+    ctx->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->sms = prop.multiProcessorCount;
+    int B = 0;
+    for (int v = 0; v < V; ++v) {
+        if (levels_per_var[v] < 1) FAIL("every covariate needs at least one level");
+        ctx->levels.push_back(levels_per_var[v]);
+        ctx->level_off.push_back(B);
+        B += levels_per_var[v];
+    }
+    st.N = n_local; st.Nglobal = n_global; st.cell_offset = cell_offset;
+    st.d = d; st.dp = (d + 3) & ~3; st.K = K; st.Kp = (K + 3) & ~3;
+    ctx->KPT = (K <= 32) ? 1 : (K <= 64) ? 2 : (K <= 128) ? 4 : 8;
+    ctx->JPW = (st.dp <= 32) ? 4 : (st.dp <= 64) ? 8 : 16;
+    st.KS = 32 * ctx->KPT;
+    st.V = V; st.B = B; st.lev0 = levels_per_var[0];
+    if (!bind_for(ctx)) FAIL("no kernel instantiation for this (K, d)");
+    // state
+    if (dev_alloc(ctx, &st.Zorig, (size_t)st.N * st.dp)) return 1;
+    if (dev_alloc(ctx, &st.Zcos, (size_t)st.N * st.dp)) return 1;
+    if (dev_alloc(ctx, &st.Zcorr, (size_t)st.N * st.dp)) return 1;
+    if (dev_alloc(ctx, &st.R, (size_t)st.N * st.Kp)) return 1;
+    if (dev_alloc(ctx, &st.combo, (size_t)st.N)) return 1;
+    if (dev_alloc(ctx, &st.order, (size_t)st.N)) return 1;
+    if (dev_alloc(ctx, &st.pos_of, (size_t)st.N)) return 1;
+    if (dev_alloc(ctx, &st.blk, (size_t)st.N)) return 1;
+    if (dev_alloc(ctx, &st.list, (size_t)st.N)) return 1;
+    if (dev_alloc(ctx, &ctx->Ybuf[0], (size_t)K * st.dp)) return 1;
+    if (dev_alloc(ctx, &ctx->Ybuf[1], (size_t)K * st.dp)) return 1;
+    if (dev_alloc(ctx, &st.P, (size_t)B * K)) return 1;
+    if (dev_alloc(ctx, &st.O, (size_t)B * K)) return 1;
+    if (dev_alloc(ctx, &st.Orun, (size_t)B * K)) return 1;
+    if (dev_alloc(ctx, &st.obj_out, 4)) return 1;
+    if (dev_alloc(ctx, &st.Pr_b, (size_t)B)) return 1;
+    if (dev_alloc(ctx, &st.theta, (size_t)B)) return 1;
+    if (dev_alloc(ctx, &st.sigma, (size_t)K)) return 1;
+    if (dev_alloc(ctx, &st.lamb, (size_t)B + 1)) return 1;
+    if (dev_alloc(ctx, &st.W, (size_t)B * K * st.dp)) return 1;
+    if (dev_alloc(ctx, &st.bar_count, 2)) return 1;
+    st.bar_gen = st.bar_count + 1;
+    CK(cudaMemset(st.bar_count, 0, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(st.O, 0, (size_t)B * K * sizeof(double)));
+    CK(cudaMemset(st.W, 0, (size_t)B * K * st.dp * sizeof(float)));
+    // ridge accumulators in one zeroable block: Gram | Mom
+    {
+        const size_t nG = (size_t)K * (B + 1) * (B + 1), nM = (size_t)(B + 1) * K * st.dp;
+        ctx->zero_ridge_bytes = (nG + nM) * sizeof(double);
+        if (dev_alloc(ctx, &ctx->zero_ridge, ctx->zero_ridge_bytes)) return 1;
+        st.Gram = (double*)ctx->zero_ridge; st.Mom = st.Gram + nG;
+    }
+    if (dev_alloc(ctx, &st.Yacc, (size_t)K * st.dp)) return 1;
+    CK(cudaMallocHost((void**)&ctx->h_obj, 4 * sizeof(double)));
+    st.Yhat = ctx->Ybuf[0]; st.Ynext = ctx->Ybuf[1]; ctx->Ylast = ctx->Ybuf[0];
+    CK(cudaMemset(ctx->Ybuf[0], 0, (size_t)K * st.dp * sizeof(float)));
+    CK(cudaMemset(ctx->Ybuf[1], 0, (size_t)K * st.dp * sizeof(float)));
+    // ridge launch shapes
+    ctx->smem_mom = ridge_smem_plan(K, st.KS, ctx->JPW, false).total;
+    ctx->smem_apply = ridge_smem_plan(K, st.KS, ctx->JPW, true).total;
+    ctx->smem_solve = (int)(((size_t)(B + 1) * (B + 1 + d) + (B + 1)) * sizeof(double));
+    if (ctx->smem_solve > 200 * 1024) FAIL("ridge system too large for shared memory ((B+1)*(B+1+d) doubles > 200 KB)");
+    CK(cudaFuncSetAttribute(ctx->fn_mom, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_mom));
+    CK(cudaFuncSetAttribute(ctx->fn_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_apply));
+    CK(cudaFuncSetAttribute((const void*)k_ridge_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_solve));
+    return 0;
+}
+
+extern "C" int hmy_create(hmy_ctx** out, int device, int64_t n_local, int64_t n_global, int64_t cell_offset,
+                          int d, int K, int V, const int32_t* levels_per_var) {
+    if (!out) { g_create_error = "hmy_create: out is NULL"; return 1; }
+    *out = nullptr;
+    hmy_ctx* ctx = new hmy_ctx();
+    if (create_impl(ctx, device, n_local, n_global, cell_offset, d, K, V, levels_per_var)) {
+        g_create_error = ctx->err;
+        hmy_destroy(ctx);
+        return 1;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void hmy_destroy(hmy_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : ctx->allocs) cudaFree(p);
+    if (ctx->d_perm) cudaFree(ctx->d_perm);
+    if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+    if (ctx->h_obj) cudaFreeHost(ctx->h_obj);
+    for (auto& e : ctx->ev_round) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& e : ctx->ev_ridge) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    delete ctx;
+}
+
+extern "C" int hmy_set_stream(hmy_ctx* ctx, void* cuda_stream) {
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+// round launch shape: depends on nblk (shared-memory plan), so fixed once block_size is known
+static int plan_round(hmy_ctx* ctx) {
+    HmyDev& st = ctx->st;
+    const int nblk = (int)std::ceil(1.0 / (double)ctx->block_size);          // harmony.py:474
+    if (nblk < 1 || nblk > HMY_MAX_NBLK) FAIL("block_size gives an unsupported number of blocks (1..250)");
+    st.nblk = nblk;
+    st.cpb = (long long)((double)st.Nglobal * (double)ctx->block_size);      // harmony.py:475
+    ctx->smem_round = round_smem_plan(st.dp, st.KS, st.B, st.V, nblk, ctx->JPW).total;
+    if (ctx->smem_round > 227 * 1024) FAIL("round kernel needs more than 227 KB of shared memory for this (K, B, d, block_size)");
+    CK(cudaFuncSetAttribute(ctx->fn_round, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
+    CK(cudaFuncSetAttribute(ctx->fn_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
+    int nb = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, HMY_THREADS, ctx->smem_round));
+    if (nb < 1) FAIL("round kernel does not fit on an SM");
+    ctx->G = nb * ctx->sms;
+    // per-round zero block: Told | Dnew | Yacc is separate (ridge also uses it) | obj
+    const size_t nT = (size_t)nblk * st.B * st.K;
+    ctx->zero_round_bytes = 2 * nT * sizeof(float) + 4 * sizeof(double);
+    ctx->zero_round_bytes = (ctx->zero_round_bytes + 7) & ~(size_t)7;
+    if (dev_alloc(ctx, &ctx->zero_round, ctx->zero_round_bytes + 8)) return 1;
+    st.obj = (double*)ctx->zero_round;                      // 8-byte aligned at the front
+    st.Told = (float*)(st.obj + 4); st.Dnew = st.Told + nT;
+    if (dev_alloc(ctx, &st.list_off, (size_t)ctx->G * (nblk + 1))) return 1;
+    int nbr = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbr, ctx->fn_apply, HMY_THREADS, ctx->smem_apply));
+    ctx->grid_ridge = std::max(1, nbr) * ctx->sms;
+    return 0;
+}
+
+extern "C" int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* theta, const float* sigma,
+                              const float* lamb, int lambda_estimation, float alpha, float block_size) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->have_params) FAIL("hmy_set_params may be called once per context");
+    if (!(block_size > 0.f) || block_size > 1.f) FAIL("block_size must be in (0, 1]");
+    ctx->block_size = block_size;
+    CK(cudaMemcpy(st.Pr_b, Pr_b, st.B * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.theta, theta, st.B * sizeof(float), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.sigma, sigma, st.K * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> l(st.B + 1, 0.f);
+    if (!lambda_estimation) { if (!lamb) FAIL("lamb is NULL"); std::copy(lamb, lamb + st.B + 1, l.begin()); }
+    CK(cudaMemcpy(st.lamb, l.data(), (st.B + 1) * sizeof(float), cudaMemcpyHostToDevice));
+    st.lambda_estimation = lambda_estimation ? 1 : 0;
+    st.alpha = alpha;
+    if (plan_round(ctx)) return 1;
+    ctx->have_params = true;
+    return 0;
+}
+
+extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* codes_host) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!Z_host || !codes_host) FAIL("hmy_set_data: NULL input");
+    const long long N = st.N; const int V = st.V;
+    // combination key of every cell (covariate 0 most significant)
+    std::vector<unsigned long long> key((size_t)N);
+    {
+        std::vector<unsigned long long> mult(V, 1ull);
+        long double span = 1.0L;
+        for (int v = V - 1; v >= 0; --v) { mult[v] = (unsigned long long)span; span *= ctx->levels[v]; }
+        if (span > 9.0e18L) FAIL("product of covariate level counts overflows 64 bits");
+        for (long long n = 0; n < N; ++n) {
+            unsigned long long k = 0;
+            for (int v = 0; v < V; ++v) {
+                const int c = codes_host[(size_t)v * N + n];
+                if (c < 0 || c >= ctx->levels[v]) FAIL("level code out of range");
+                k += (unsigned long long)c * mult[v];
+            }
+            key[n] = k;
+        }
+    }
+    std::vector<int> order((size_t)N);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    std::vector<int> pos_of((size_t)N), combo((size_t)N), combo_lev;
+    std::vector<long long> combo_start;
+    int ncombo = 0;
+    for (long long p = 0; p < N; ++p) {
+        const int src = order[p];
+        pos_of[src] = (int)p;
+        if (p == 0 || key[src] != key[order[p - 1]]) {
+            combo_start.push_back(p);
+            for (int v = 0; v < V; ++v) combo_lev.push_back(ctx->level_off[v] + codes_host[(size_t)v * N + src]);
+            ++ncombo;
+        }
+        combo[p] = ncombo - 1;
+    }
+    combo_start.push_back(N);
+    st.ncombo = ncombo;
+    // ridge work items: <= HMY_SEG_MAX consecutive cells of one combination
+    std::vector<int> seg;
+    for (int c = 0; c < ncombo; ++c)
+        for (long long s = combo_start[c]; s < combo_start[c + 1]; s += HMY_SEG_MAX) {
+            seg.push_back((int)s); seg.push_back((int)std::min<long long>(HMY_SEG_MAX, combo_start[c + 1] - s)); seg.push_back(c);
+        }
+    st.nseg = (int)(seg.size() / 3);
+    if (dev_alloc(ctx, &st.combo_lev, combo_lev.size())) return 1;
+    if (dev_alloc(ctx, &st.combo_start, combo_start.size())) return 1;
+    if (dev_alloc(ctx, &st.seg, seg.size())) return 1;
+    CK(cudaMemcpy(st.combo_lev, combo_lev.data(), combo_lev.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.combo_start, combo_start.data(), combo_start.size() * sizeof(long long), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.combo, combo.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.order, order.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(st.pos_of, pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    // raw rows -> sorted padded layout + Z_cos
+    float* raw = nullptr;
+    CK(cudaMalloc((void**)&raw, (size_t)N * st.d * sizeof(float)));
+    cudaError_t e = cudaMemcpyAsync(raw, Z_host, (size_t)N * st.d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+        const long long threads = N * 32;
+        k_ingest<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(st, raw);
+        ctx->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(raw);
+    CK(e);
+    ctx->have_data = true;
+    return 0;
+}
+
+// ---- helpers ------------------------------------------------------------------------------
+static int launch(hmy_ctx* ctx, const void* fn, dim3 grid, dim3 block, void** args, size_t smem, bool coop) {
+    if (coop) CK(cudaLaunchCooperativeKernel(fn, grid, block, args, smem, ctx->stream));
+    else CK(cudaLaunchKernel(fn, grid, block, args, smem, ctx->stream));
+    ctx->launches++;
+    return 0;
+}
+
+static int allreduce(hmy_ctx* ctx, void* p, int64_t count, int dtype) {
+    if (!ctx->ar) return 0;
+    if (ctx->ar(ctx->ar_user, p, count, dtype, (void*)ctx->stream)) FAIL("all-reduce callback failed");
+    return 0;
+}
+
+static int timer_begin(hmy_ctx* ctx, std::vector<EventPair>& v) {
+    if (!ctx->timing) return 0;
+    EventPair p;
+    CK(cudaEventCreate(&p.a)); CK(cudaEventCreate(&p.b));
+    CK(cudaEventRecord(p.a, ctx->stream));
+    v.push_back(p);
+    return 0;
+}
+static int timer_end(hmy_ctx* ctx, std::vector<EventPair>& v) {
+    if (!ctx->timing) return 0;
+    CK(cudaEventRecord(v.back().b, ctx->stream));
+    return 0;
+}
+static void timer_collect(std::vector<EventPair>& v, double& acc) {
+    for (auto& p : v) {
+        cudaEventSynchronize(p.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) acc += ms;
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    v.clear();
+}
+
+static int fetch_obj(hmy_ctx* ctx, double obj[3]) {
+    CK(cudaMemcpyAsync(ctx->h_obj, ctx->st.obj_out, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (obj) { obj[0] = ctx->h_obj[0]; obj[1] = ctx->h_obj[1]; obj[2] = ctx->h_obj[2]; }
+    return 0;
+}
+
+static void swap_centroids(hmy_ctx* ctx) {
+    ctx->Ylast = ctx->Ybuf[ctx->ycur];
+    ctx->ycur ^= 1;
+    ctx->st.Yhat = ctx->Ybuf[ctx->ycur];
+    ctx->st.Ynext = ctx->Ybuf[ctx->ycur ^ 1];
+}
+
+static int staged_tables(hmy_ctx* ctx, int what, int blk) {
+    HmyDev st = ctx->st;
+    void* args[] = {&st, &what, &blk};
+    return launch(ctx, (const void*)k_tables, dim3(1), dim3(HMY_THREADS), args, 0, false);
+}
+static int staged_round(hmy_ctx* ctx, int what, int blk) {
+    HmyDev st = ctx->st;
+    void* args[] = {&st, &what, &blk};
+    return launch(ctx, ctx->fn_stage, dim3(ctx->G), dim3(HMY_THREADS), args, ctx->smem_round, false);
+}
+
+// ---- a2: init ------------------------------------------------------------------------------
+extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj[3]) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_data || !ctx->have_params) FAIL("hmy_init_from_centroids: set params and data first");
+    // unit-length centroids (harmony.py:377), K x dp zero padded
+    std::vector<float> Y((size_t)st.K * st.dp, 0.f);
+    for (int k = 0; k < st.K; ++k) {
+        double ss = 0.0;
+        for (int j = 0; j < st.d; ++j) ss += (double)Y0[(size_t)k * st.d + j] * Y0[(size_t)k * st.d + j];
+        const double inv = 1.0 / std::sqrt(ss);
+        for (int j = 0; j < st.d; ++j) Y[(size_t)k * st.dp + j] = (float)(Y0[(size_t)k * st.d + j] * inv);
+    }
+    CK(cudaMemcpyAsync(st.Yhat, Y.data(), Y.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // Y is a stack-lifetime host buffer
+    CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
+    CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
+    if (timer_begin(ctx, ctx->ev_round)) return 1;
+    if (ctx->persistent && !ctx->ar) {
+        HmyDev s = st; int mode = 1; unsigned int gen = ctx->gen;
+        void* args[] = {&s, &mode, &gen};
+        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(HMY_THREADS), args, ctx->smem_round, true)) return 1;
+        ctx->gen += 1;
+    } else {
+        if (staged_round(ctx, 2, 0)) return 1;
+        if (allreduce(ctx, st.Dnew, (int64_t)st.B * st.K, 0)) return 1;
+        if (allreduce(ctx, st.Yacc, (int64_t)st.K * st.dp, 1)) return 1;
+        if (allreduce(ctx, st.obj, 4, 1)) return 1;
+        if (staged_tables(ctx, 2, 1)) return 1;
+    }
+    if (timer_end(ctx, ctx->ev_round)) return 1;
+    swap_centroids(ctx);
+    ctx->have_init = true;
+    return fetch_obj(ctx, obj);
+}
+
+// ---- a3/a4/a5: one k-means round -----------------------------------------------------------
+extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double obj[3]) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_init) FAIL("hmy_kmeans_round: call hmy_init_from_centroids first");
+    // block of every cell for this round (harmony.py:471-475)
+    if (perm_host) {
+        if (!ctx->d_perm) CK(cudaMalloc((void**)&ctx->d_perm, (size_t)st.Nglobal * sizeof(long long)));
+        CK(cudaMemcpyAsync(ctx->d_perm, perm_host, (size_t)st.Nglobal * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        k_assign_from_perm<<<(unsigned int)((st.Nglobal + 255) / 256), 256, 0, ctx->stream>>>(st, ctx->d_perm);
+    } else {
+        int hb = 1;
+        while ((1ull << (2 * hb)) < (unsigned long long)st.Nglobal) ++hb;
+        k_assign_feistel<<<(unsigned int)((st.N + 255) / 256), 256, 0, ctx->stream>>>(st, ctx->seed, ctx->round_counter, hb);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->round_counter++;
+    CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
+    CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
+    if (timer_begin(ctx, ctx->ev_round)) return 1;
+    if (ctx->persistent && !ctx->ar) {
+        HmyDev s = st; int mode = 0; unsigned int gen = ctx->gen;
+        void* args[] = {&s, &mode, &gen};
+        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(HMY_THREADS), args, ctx->smem_round, true)) return 1;
+        ctx->gen += (unsigned int)st.nblk + 1u;
+    } else {
+        const int64_t nT = (int64_t)st.nblk * st.B * st.K, BK = (int64_t)st.B * st.K;
+        if (staged_round(ctx, 0, 0)) return 1;
+        if (allreduce(ctx, st.Told, nT, 0)) return 1;
+        if (staged_tables(ctx, 0, 0)) return 1;
+        for (int blk = 0; blk < st.nblk; ++blk) {
+            if (staged_round(ctx, 1, blk)) return 1;
+            if (allreduce(ctx, st.Dnew + (size_t)blk * BK, BK, 0)) return 1;
+            if (blk + 1 < st.nblk && staged_tables(ctx, 1, blk + 1)) return 1;
+        }
+        if (allreduce(ctx, st.Yacc, (int64_t)st.K * st.dp, 1)) return 1;
+        if (allreduce(ctx, st.obj, 4, 1)) return 1;
+        if (staged_tables(ctx, 2, 0)) return 1;
+    }
+    if (timer_end(ctx, ctx->ev_round)) return 1;
+    swap_centroids(ctx);
+    ctx->rounds++;
+    return fetch_obj(ctx, obj);
+}
+
+// ---- a7: ridge correction -------------------------------------------------------------------
+extern "C" int hmy_ridge_correct(hmy_ctx* ctx) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_init) FAIL("hmy_ridge_correct: call hmy_init_from_centroids first");
+    CK(cudaMemsetAsync(ctx->zero_ridge, 0, ctx->zero_ridge_bytes, ctx->stream));
+    CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
+    if (timer_begin(ctx, ctx->ev_ridge)) return 1;
+    const int grid = std::min(ctx->grid_ridge, std::max(1, st.nseg));
+    {
+        HmyDev s = st; void* args[] = {&s};
+        if (launch(ctx, ctx->fn_mom, dim3(grid), dim3(HMY_THREADS), args, ctx->smem_mom, false)) return 1;
+    }
+    {
+        const int64_t nG = (int64_t)st.K * (st.B + 1) * (st.B + 1), nM = (int64_t)(st.B + 1) * st.K * st.dp;
+        if (allreduce(ctx, st.Gram, nG + nM, 1)) return 1;
+    }
+    {
+        HmyDev s = st; void* args[] = {&s};
+        if (launch(ctx, (const void*)k_ridge_solve, dim3(st.K), dim3(128), args, ctx->smem_solve, false)) return 1;
+    }
+    {
+        HmyDev s = st; void* args[] = {&s};
+        if (launch(ctx, ctx->fn_apply, dim3(grid), dim3(HMY_THREADS), args, ctx->smem_apply, false)) return 1;
+    }
+    if (allreduce(ctx, st.Yacc, (int64_t)st.K * st.dp, 1)) return 1;
+    {
+        // centroids the next cluster() starts from (harmony.py:443 with the new Z_cos): they
+        // replace the pending ones, not the ones the last round used
+        HmyDev s = st; s.Ynext = st.Yhat;
+        int what = 2, mode = 2;
+        void* args[] = {&s, &what, &mode};
+        if (launch(ctx, (const void*)k_tables, dim3(1), dim3(HMY_THREADS), args, 0, false)) return 1;
+    }
+    if (timer_end(ctx, ctx->ev_ridge)) return 1;
+    ctx->ridge_passes++;
+    return 0;
+}
+
+// ---- property reads --------------------------------------------------------------------------
+static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_out, int64_t bytes) {
+    HmyDev& st = ctx->st;
+    const size_t need = (size_t)st.N * w * sizeof(float);
+    if ((size_t)bytes != need) FAIL("hmy_get: wrong buffer size");
+    if (ctx->tmp_bytes < need) {
+        if (ctx->d_tmp) cudaFree(ctx->d_tmp);
+        ctx->d_tmp = nullptr; ctx->tmp_bytes = 0;
+        CK(cudaMalloc((void**)&ctx->d_tmp, need));
+        ctx->tmp_bytes = need;
+    }
+    const long long threads = st.N * 32;
+    k_unsort_rows<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(src, sp, ctx->d_tmp, w, st.order, st.N);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(host_out, ctx->d_tmp, need, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!host_out) FAIL("hmy_get: NULL output");
+    switch (which) {
+        case HMY_Z_CORR: return get_cells(ctx, st.Zcorr, st.dp, st.d, host_out, bytes);
+        case HMY_Z_COS: return get_cells(ctx, st.Zcos, st.dp, st.d, host_out, bytes);
+        case HMY_Z_ORIG: return get_cells(ctx, st.Zorig, st.dp, st.d, host_out, bytes);
+        case HMY_R: return get_cells(ctx, st.R, st.Kp, st.K, host_out, bytes);
+        case HMY_Y: {
+            if ((size_t)bytes != (size_t)st.K * st.d * sizeof(float)) FAIL("hmy_get(Y): wrong buffer size");
+            std::vector<float> t((size_t)st.K * st.dp);
+            CK(cudaMemcpyAsync(t.data(), ctx->Ylast, t.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float* o = (float*)host_out;
+            for (int k = 0; k < st.K; ++k) for (int j = 0; j < st.d; ++j) o[(size_t)k * st.d + j] = t[(size_t)k * st.dp + j];
+            return 0;
+        }
+        case HMY_O: case HMY_E: {
+            if ((size_t)bytes != (size_t)st.K * st.B * sizeof(double)) FAIL("hmy_get(O/E): wrong buffer size");
+            std::vector<double> t((size_t)st.B * st.K);
+            std::vector<float> pr(st.B);
+            CK(cudaMemcpyAsync(t.data(), st.O, t.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaMemcpyAsync(pr.data(), st.Pr_b, st.B * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            double* o = (double*)host_out;
+            for (int k = 0; k < st.K; ++k) {
+                double rs = 0.0;
+                for (int b = 0; b < st.lev0; ++b) rs += t[(size_t)b * st.K + k];
+                for (int b = 0; b < st.B; ++b)
+                    o[(size_t)k * st.B + b] = (which == HMY_O) ? t[(size_t)b * st.K + k] : rs * (double)pr[b];   // E: harmony.py:388
+            }
+            return 0;
+        }
+        case HMY_W: {
+            const size_t n = (size_t)st.B * st.K * st.d;
+            if ((size_t)bytes != n * sizeof(float)) FAIL("hmy_get(W): wrong buffer size");
+            std::vector<float> t((size_t)st.B * st.K * st.dp);
+            CK(cudaMemcpyAsync(t.data(), st.W, t.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            float* o = (float*)host_out;
+            for (size_t r = 0; r < (size_t)st.B * st.K; ++r) for (int j = 0; j < st.d; ++j) o[r * st.d + j] = t[r * st.dp + j];
+            return 0;
+        }
+    }
+    FAIL("hmy_get: unknown matrix id");
+}
+
+extern "C" int hmy_synchronize(hmy_ctx* ctx) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
+    const std::string n(name ? name : "");
+    if (n == "persistent") { ctx->persistent = value != 0; return 0; }
+    if (n == "seed") { ctx->seed = (unsigned long long)value * 0x9E3779B97F4A7C15ull + 0x243F6A8885A308D3ull; ctx->round_counter = 0; return 0; }
+    if (n == "timing") { ctx->timing = value != 0; return 0; }
+    FAIL("hmy_set_option: unknown option");
+}
+
+extern "C" int64_t hmy_counter(const hmy_ctx* ctx, const char* name) {
+    const std::string n(name ? name : "");
+    if (n == "launches") return ctx->launches;
+    if (n == "rounds") return ctx->rounds;
+    if (n == "ridge_passes") return ctx->ridge_passes;
+    if (n == "grid") return ctx->G;
+    if (n == "smem_round") return ctx->smem_round;
+    if (n == "nblk") return ctx->st.nblk;
+    if (n == "ncombo") return ctx->st.ncombo;
+    return -1;
+}
+
+extern "C" double hmy_timer_ms(hmy_ctx* ctx, const char* name) {
+    const std::string n(name ? name : "");
+    cudaSetDevice(ctx->device);
+    timer_collect(ctx->ev_round, ctx->ms_round);
+    timer_collect(ctx->ev_ridge, ctx->ms_ridge);
+    if (n == "ms_round") return ctx->ms_round;
+    if (n == "ms_ridge") return ctx->ms_ridge;
+    return -1.0;
+}
+
+extern "C" int hmy_set_allreduce(hmy_ctx* ctx, hmy_allreduce_fn fn, void* user) {
+    ctx->ar = fn; ctx->ar_user = user;
+    return 0;
+}
+
+extern "C" int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B) {
+    (void)handle_out_64B;
+    FAIL("hmy_comm_export: fused peer exchange is not built in this version");
+}
+
+extern "C" int hmy_comm_attach(hmy_ctx* ctx, int rank, int world, const void* all_handles) {
+    (void)rank; (void)world; (void)all_handles;
+    FAIL("hmy_comm_attach: fused peer exchange is not built in this version");
+}

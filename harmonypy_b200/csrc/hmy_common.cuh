@@ -1,0 +1,109 @@
+// Shared device-side definitions for the Harmony engine (sm_100a).
+//
+// HBM layout (all cell-major, cells physically sorted by covariate combination so that
+// every contiguous run of cells shares its batch levels -- see DESIGN.md "Data layout"):
+//   Zorig, Zcos, Zcorr : [N][dp]  fp32, dp = round_up(d, 4), zero padded (16-byte rows)
+//   R                  : [N][Kp]  fp32, Kp = round_up(K, 4)
+//   combo              : [N]      int32 id of the covariate combination of the cell
+//   combo_lev          : [ncombo][V] int32 global one-hot row of each covariate's level
+//   blk                : [N]      uint8 update block of the cell in the current round
+// Small tables (L2 / shared-memory resident):
+//   Yhat [K][dp] fp32 unit centroids, Yacc [K][dp] fp64 centroid sums,
+//   Told/Dnew [nblk][B][K] fp32 per-block removed / re-added batch sums,
+//   P [B][K] fp32 diversity penalty, O/Orun [B][K] fp64, obj[4] fp64.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HMY_THREADS 256
+#define HMY_WARPS 8
+#define HMY_TILE 64          // cells per tile in every streaming kernel
+#define HMY_CPW 8            // cells per warp inside a tile (HMY_TILE / HMY_WARPS)
+#define HMY_MAX_V 8
+#define HMY_MAX_NBLK 250
+
+struct HmyDev {
+    long long N;             // cells on this rank
+    long long Nglobal;
+    long long cell_offset;
+    long long cpb;           // int(Nglobal * block_size), harmony.py:475
+    int d, dp, K, Kp, KS;    // KS = 32 * KPT, shared-memory stride over clusters
+    int V, B, nblk, ncombo;
+    int lev0;                // levels of covariate 0 (their one-hot rows are [0, lev0))
+    int nseg;                // ridge work items
+    int lambda_estimation;
+    float alpha;
+    // cell-major state
+    float* Zorig; float* Zcos; float* Zcorr; float* R;
+    int* combo; int* combo_lev; long long* combo_start;   // [ncombo+1] first cell of each combo
+    int* order;              // order[pos] = caller's local index of the cell stored at pos
+    int* pos_of;             // inverse of order
+    unsigned char* blk;
+    int* list; int* list_off;            // per-CTA block lists, list_off[G][nblk+1]
+    int* seg;                            // ridge work items: [nseg][3] = start, count, combo
+    // tables
+    float* Yhat; float* Ynext; double* Yacc;   // Yhat: centroids this stage reads; Ynext: the ones it produces
+    float* Told; float* Dnew; float* P;
+    double* O; double* Orun;             // [B][K]
+    double* obj;                         // [0..2] objective sums, [3] spare
+    double* obj_out;                     // [3] finished objective of the last stage
+    float* Pr_b; float* theta; float* sigma; float* lamb;   // lamb[B+1]
+    double* Gram;            // [K][B+1][B+1]
+    double* Mom;             // [B+1][K][dp]
+    float* W;                // [B][K][dp]
+    // grid barrier
+    unsigned int* bar_count; unsigned int* bar_gen;
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid-wide barrier with a serial section: every CTA arrives; the LAST one to arrive runs
+// `serial()` (all of its threads) and then releases generation `gen`; the others wait.
+// Requires all CTAs of the grid to be co-resident (cooperative launch).
+template <class F>
+__device__ __forceinline__ void grid_barrier_serial(const HmyDev& st, unsigned int nctas,
+                                                    unsigned int gen, int* s_flag, F serial) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(st.bar_count, 1u);
+        *s_flag = (t == nctas - 1u);
+    }
+    __syncthreads();
+    if (*s_flag) {
+        __threadfence();
+        serial();
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *st.bar_count = 0u;
+            __threadfence();
+            st_release_u32(st.bar_gen, gen);
+        }
+    } else {
+        if (threadIdx.x == 0) {
+            while ((int)(ld_acquire_u32(st.bar_gen) - gen) < 0) { __nanosleep(20); }
+        }
+    }
+    __syncthreads();
+}
