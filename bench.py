@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the Harmony hot path (cluster() + moe_correct_ridge() to convergence).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload NAME]
+
+Metric (BASELINE.json): cells/sec to convergence of the full Harmony loop.
+A *step* = one complete run of the loop from the post-upload state: restore Z_cos, the
+init assignment from given centroids (harmony.py:377-392) and harmonize() until the
+reference's own convergence rule stops it (harmony.py:419-435) -- nothing skipped.
+The k-means++ initialisation (sklearn, harmony.py:369-373) is outside the hot path and is
+computed once, untimed, on a 100k-cell subsample; both arms start from the same centroids.
+
+  value      whole-job cells/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through run_harmony(...) with HOST arrays: H2D upload, layout
+             sort, loop, D2H of Z_corr inside the timed region
+  roofline   HBM roofline of the dominant kernel (k_round), from CUDA events recorded by
+             the library around every round launch (live, this run)
+  cpu_baseline  the CPU oracle (NumPy port of the reference's algorithm) on a bounded
+             sample of the same workload, on this box's host cores
+
+Workloads (BASELINE.json configs): syn1m (default; 1M cells x 50 PCs x 20 batches, K=100,
+per GPU -- weak scaling), syn10m8 (10M x 50 x 50 batches over 8 GPUs => 1.25M per GPU),
+syn5m8 (5M x 50, covariates 30+4, K=200 over 8 GPUs => 625k per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "syn1m": dict(per_gpu=1_000_000, d=50, levels=[20], K=100,
+                  name="synthetic 1M cells x 50 PCs x 20 batches, K=100 (per GPU)"),
+    "syn10m8": dict(per_gpu=1_250_000, d=50, levels=[50], K=100,
+                    name="synthetic 10M cells x 50 PCs x 50 batches, K=100 over 8 GPUs (1.25M per GPU)"),
+    "syn5m8": dict(per_gpu=625_000, d=50, levels=[30, 4], K=200,
+                   name="synthetic 5M cells x 50 PCs, covariates 30+4, K=200 over 8 GPUs (625k per GPU)"),
+    "tiny": dict(per_gpu=50_000, d=50, levels=[20], K=100, name="tiny debug workload (50k cells per GPU)"),
+}
+SEED = 0
+INIT_SUBSAMPLE = 100_000
+
+
+def algorithmic_bytes(d, K, V):
+    """bytes per cell of one k-means round / one ridge pass."""
+    return 4 * d + 8 * K + 4 * V + 4, 16 * d + 8 * K + 8 * V
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def init_centroids(w, N_total, seed=SEED):
+    """k-means++ / 25 Lloyd iterations (the reference's sklearn settings, harmony.py:370-371)
+    on the unit-normalised first INIT_SUBSAMPLE cells.  Untimed; identical for both arms."""
+    from sklearn.cluster import KMeans
+    from harmonypy_b200.synthetic import make_synthetic_arrays
+    n = min(N_total, INIT_SUBSAMPLE)
+    Z, _ = make_synthetic_arrays(N_total, w["d"], w["levels"], seed=seed, lo=0, hi=n)
+    Zc = Z / np.linalg.norm(Z, axis=1, keepdims=True)
+    km = KMeans(n_clusters=w["K"], init="k-means++", n_init=1, max_iter=25, random_state=seed).fit(Zc)
+    return km.cluster_centers_.astype(np.float32)
+
+
+def global_level_probs(w, N_total, lo, hi, codes, dist=None):
+    counts = np.concatenate([np.bincount(codes[v], minlength=int(b)) for v, b in enumerate(w["levels"])]).astype(np.float64)
+    if dist is not None:
+        import torch
+        t = torch.from_numpy(counts).cuda()
+        dist.all_reduce(t)
+        counts = t.cpu().numpy()
+    return (counts / N_total).astype(np.float32)
+
+
+def make_problem(w, Z, codes, Pr_b, N_total, lo):
+    from harmonypy_b200.harmony import Problem
+    levels = np.asarray(w["levels"], dtype=np.int32)
+    B = int(levels.sum())
+    return Problem(Z=Z, codes=codes, levels=levels, level_names=[], Pr_b=Pr_b,
+                   theta=np.full(B, 2, np.float32), lamb=np.concatenate([[0], np.ones(B)]).astype(np.float32),
+                   lambda_estimation=False, sigma=np.full(w["K"], 0.1, np.float32), K=w["K"],
+                   n_global=N_total, shard_lo=lo)
+
+
+def harmony_step(ho, Y0):
+    """One full run of the hot path on an engine that already holds the data."""
+    ho._engine.set_option("reset", 1)
+    for lst in (ho.objective_harmony, ho.objective_kmeans, ho.objective_kmeans_dist, ho.objective_kmeans_entropy,
+                ho.objective_kmeans_cross, ho.kmeans_rounds):
+        lst.clear()
+    ho.init_cluster(SEED, Y0)
+    ho.harmonize(ho.max_iter_harmony, False)
+    return sum(ho.kmeans_rounds), len(ho.kmeans_rounds)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(w, Y0, n_sample, max_seconds=None):
+    """Oracle port of the reference's CPU algorithm on the first n_sample cells of the
+    workload: init assignment + harmonize to convergence.  Returns (cells/s, seconds, info)."""
+    from harmonypy_b200.synthetic import make_synthetic_arrays
+    from oracle.harmony_oracle import HarmonyOracle, onehot_from_codes, torch_perm_source
+    Z, codes = make_synthetic_arrays(max(n_sample, 1), w["d"], w["levels"], seed=SEED, lo=0, hi=n_sample)
+    levels = np.asarray(w["levels"])
+    B = int(levels.sum())
+    Pr_b = np.concatenate([np.bincount(codes[v], minlength=int(b)) for v, b in enumerate(levels)]) / n_sample
+    phi = onehot_from_codes(codes, levels, np.float32)
+    orc = HarmonyOracle(Z.T, phi, Pr_b.astype(np.float32), np.full(w["K"], 0.1, np.float32), np.full(B, 2, np.float32),
+                        np.concatenate([[0], np.ones(B)]).astype(np.float32), dtype=np.float32)
+    t0 = time.perf_counter()
+    orc.init_from_centroids(Y0.T)
+    orc.harmonize(10, torch_perm_source(n_sample, SEED))
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt, dict(rounds=list(map(int, orc.kmeans_rounds)))
+
+
+def run_reference(args, w):
+    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is
+    Python and cannot travel to this box) on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = args.cpu_sample
+    Y0 = init_centroids(w, n_sample)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt, info = cpu_oracle_rate(w, Y0, n_sample)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = n_sample / (ms / 1e3)
+    cores = os.cpu_count()
+    out = {
+        "impl": "reference", "metric": "cells/sec to convergence (full Harmony loop)", "value": val,
+        "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": f"first {n_sample} cells of the workload", "K": w["K"], "d": w["d"],
+                   "levels": w["levels"], "rounds": info["rounds"]},
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
+                         "sample": f"oracle/harmony_oracle.py (NumPy, fp32) on the first {n_sample} cells; "
+                                   "init assignment + harmonize to convergence"},
+        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, w):
+    import torch
+    from harmonypy_b200.build import build
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if rank == 0:
+        build(verbose=False)
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    from harmonypy_b200.harmony import Harmony, Comm
+    from harmonypy_b200.synthetic import make_synthetic_arrays
+
+    N_total = w["per_gpu"] * world
+    lo, hi = N_total * rank // world, N_total * (rank + 1) // world
+    t_setup = time.perf_counter()
+    Z, codes = make_synthetic_arrays(N_total, w["d"], w["levels"], seed=SEED, lo=lo, hi=hi)
+    Pr_b = global_level_probs(w, N_total, lo, hi, codes, dist)
+    if rank == 0:
+        Y0 = init_centroids(w, N_total)
+    else:
+        Y0 = np.zeros((w["K"], w["d"]), np.float32)
+    comm = None
+    if world > 1:
+        comm = Comm(None)
+        Y0 = comm.broadcast_array(Y0, 0)
+    prob = make_problem(w, Z, codes, Pr_b, N_total, lo)
+    opts = {"persistent": 0} if args.staged else None
+    ho = Harmony(prob, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, SEED, local_rank, perm_mode="device",
+                 comm=comm, engine_options=opts, run=False)
+    eng = ho._engine
+    t_setup = time.perf_counter() - t_setup
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        harmony_step(ho, Y0)
+    barrier()
+    l0, r0, p0 = eng.counter("launches"), eng.counter("rounds"), eng.counter("ridge_passes")
+    ms_round0, ms_ridge0, ms_init0 = eng.timer_ms("ms_round"), eng.timer_ms("ms_ridge"), eng.timer_ms("ms_init")
+    stream = torch.cuda.default_stream()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record(stream)
+        tot_rounds = tot_iters = 0
+        for _ in range(args.steps):
+            r, it = harmony_step(ho, Y0)
+            tot_rounds += r; tot_iters += it
+        e1.record(stream)
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    launches = eng.counter("launches") - l0
+    n_rounds, n_ridge = eng.counter("rounds") - r0, eng.counter("ridge_passes") - p0
+    ms_round = eng.timer_ms("ms_round") - ms_round0
+    ms_ridge = eng.timer_ms("ms_ridge") - ms_ridge0
+    ms_init = eng.timer_ms("ms_init") - ms_init0
+    ms_per_step = ms_total / args.steps
+    value = N_total / (ms_per_step / 1e3)
+
+    # ---- roofline of the dominant kernel (k_round), live numbers from this run
+    V = len(w["levels"])
+    b_round, b_ridge = algorithmic_bytes(w["d"], w["K"], V)
+    n_local = hi - lo
+    peak, peak_src = measured_peak_gbs()
+    ach_round = (b_round * n_local * n_rounds) / (ms_round / 1e3) / 1e9 if ms_round > 0 else 0.0
+    ach_ridge = (b_ridge * n_local * n_ridge) / (ms_ridge / 1e3) / 1e9 if ms_ridge > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("workload") == args.workload:
+            traffic = tj.get("k_round_dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_round (one k-means round, persistent cooperative kernel)",
+                "achieved": ach_round, "peak": peak, "unit": "GB/s", "frac": ach_round / peak, "traffic": traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_cell": b_round,
+                "bytes_per_launch": b_round * n_local, "avg_launch_ms": ms_round / max(n_rounds, 1),
+                "launches_timed": n_rounds, "share_of_step": ms_round / ms_total,
+                "ridge": {"achieved": ach_ridge, "frac": ach_ridge / peak, "algorithmic_bytes_per_cell": b_ridge,
+                          "avg_pass_ms": ms_ridge / max(n_ridge, 1), "share_of_step": ms_ridge / ms_total},
+                "init_share_of_step": ms_init / ms_total}
+
+    # ---- e2e through the public API with host buffers (rank-local shard in, local Z_corr out)
+    e2e = None
+    if not args.no_e2e:
+        from harmonypy_b200.harmony import Harmony as H
+        times = []
+        for i in range(2):
+            barrier()
+            t0 = time.perf_counter()
+            h2 = H(prob, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, SEED, local_rank, perm_mode="device", comm=comm,
+                   engine_options=opts, init_centroids=Y0, run=True)
+            out = h2.result_local()
+            barrier()
+            times.append(time.perf_counter() - t0)
+            del h2
+        t_e2e = min(times)
+        if dist is not None:
+            t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": N_total / t_e2e, "unit": "cells/s", "seconds": t_e2e,
+               "h2d_bytes_per_step": int(Z.nbytes + codes.nbytes + 3 * n_local * 4),
+               "d2h_bytes_per_step": int(out.nbytes),
+               "note": "Harmony(problem, ..., init_centroids) on host arrays: H2D upload, layout sort, "
+                       "init assignment, harmonize to convergence, D2H of Z_corr; best of 2"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rate, dt, info = cpu_oracle_rate(w, Y0, args.cpu_sample)
+        cpu = {"value": rate, "unit": "cells/s", "cores": os.cpu_count(), "kind": "port", "seconds": dt,
+               "sample": f"oracle/harmony_oracle.py (NumPy fp32 port of harmony.py) on the first {args.cpu_sample} "
+                         f"cells of the workload, init assignment + harmonize to convergence, rounds {info['rounds']}"}
+
+    if rank == 0:
+        out = {
+            "metric": "cells/sec to convergence (full Harmony loop)", "value": value, "unit": "cells/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["name"], "cells_total": N_total, "cells_per_gpu": w["per_gpu"], "d": w["d"],
+                       "levels": w["levels"], "K": w["K"], "parallelism": f"cells sharded over {world} GPU(s)",
+                       "perm_mode": "device", "l2": "inputs larger than L2 (R 400 MB + Z 600 MB per GPU), no flush",
+                       "init": f"sklearn k-means++ on a {min(N_total, INIT_SUBSAMPLE)}-cell subsample, untimed",
+                       "iterations_per_step": tot_iters / args.steps, "rounds_per_step": tot_rounds / args.steps,
+                       "mode": "staged launches" if args.staged else "persistent round kernel"},
+            "cell_rounds_per_s": n_local * world * n_rounds / (ms_round / 1e3) if ms_round > 0 else None,
+            "ridge_passes_per_s": n_local * world * n_ridge / (ms_ridge / 1e3) if ms_ridge > 0 else None,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks.summary(), "setup_seconds": t_setup,
+        }
+        print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="syn1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-sample", type=int, default=20_000)
+    ap.add_argument("--staged", action="store_true", help="one launch per block step instead of the persistent kernel")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+    else:
+        run_ours(args, w)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,7 +57,7 @@ def _compile(job):
 def build(force=False, jobs=None, verbose=True):
     os.makedirs(OBJ, exist_ok=True)
     digest = _sources_digest()
-    stamp = os.path.join(OBJ, "stamp")
+    stamp = LIB + ".stamp"
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB
     work = [(os.path.join(CSRC, "hmy_api.cu"), os.path.join(OBJ, "hmy_api.o"), [])]

@@ -328,6 +328,23 @@ __global__ void k_ingest(HmyDev st, const float* Zraw) {
     }
 }
 
+// back to the state right after hmy_set_data: Z_corr = Z_orig, Z_cos = unit(Z_orig) (harmony.py:234-238)
+__global__ void k_reset(HmyDev st) {
+    const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (p >= st.N) return;
+    const float* src = st.Zorig + (size_t)p * st.dp;
+    float ss = 0.f;
+    for (int j = lane; j < st.dp; j += 32) { const float z = src[j]; ss += z * z; }
+    ss = warp_sum(ss);
+    const float nrm = sqrtf(ss);
+    for (int j = lane; j < st.dp; j += 32) {
+        const float z = src[j];
+        st.Zcorr[(size_t)p * st.dp + j] = z;
+        st.Zcos[(size_t)p * st.dp + j] = z / nrm;
+    }
+}
+
 // dst[order[p]][0..w) = src[p][0..w)   (src row stride sp)
 __global__ void k_unsort_rows(const float* src, int sp, float* dst, int w, const int* order, long long N) {
     const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;

@@ -48,10 +48,14 @@ class Problem:
     lambda_estimation: bool
     sigma: np.ndarray             # K float32
     K: int
+    # Pre-sharded input (multi-GPU, large N): Z / codes hold only cells
+    # [shard_lo, shard_lo + len(Z)) of n_global cells; Pr_b must be the GLOBAL proportions.
+    n_global: int = None
+    shard_lo: int = None
 
     @property
     def N(self):
-        return self.Z.shape[0]
+        return self.Z.shape[0] if self.n_global is None else int(self.n_global)
 
     @property
     def d(self):
@@ -298,7 +302,10 @@ class Harmony:
         elif comm is not None and not isinstance(comm, Comm):
             comm = Comm(comm)
         self.comm = comm
-        self._lo, self._hi = (0, self.N) if comm is None else comm.shard(self.N)
+        if problem.shard_lo is not None:
+            self._lo, self._hi = int(problem.shard_lo), int(problem.shard_lo) + problem.Z.shape[0]
+        else:
+            self._lo, self._hi = (0, self.N) if comm is None else comm.shard(self.N)
 
         self.objective_harmony = []
         self.objective_kmeans = []
@@ -397,11 +404,18 @@ class Harmony:
         """harmony.py:353-355."""
         return self.Z_corr
 
+    def result_local(self):
+        """This rank's rows of Z_corr (cells [lo, hi) of the global order), no gather."""
+        return self._engine.get(_cabi.Z_CORR)
+
     # ------------------------------------------------------------------ stages
     def allocate_buffers(self):
         """Upload this rank's cells; the engine owns all device buffers (harmony.py:357-364)."""
         p = self.problem
-        self._engine.set_data(p.Z[self._lo:self._hi], p.codes[:, self._lo:self._hi])
+        if p.shard_lo is not None:
+            self._engine.set_data(p.Z, p.codes)
+        else:
+            self._engine.set_data(p.Z[self._lo:self._hi], p.codes[:, self._lo:self._hi])
 
     def _record_objective(self, triple):
         """Bookkeeping of compute_objective (harmony.py:396, :413-417)."""
@@ -426,6 +440,8 @@ class Harmony:
         if init_centroids is None:
             if self.comm is None or self.comm.rank == 0:
                 from sklearn.cluster import KMeans
+                if self.problem.shard_lo is not None:
+                    raise ValueError("pre-sharded input needs init_centroids (no rank holds all cells)")
                 Z = self.problem.Z
                 Z_cos = Z / np.linalg.norm(Z, axis=1, keepdims=True)
                 if self.verbose:
