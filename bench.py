@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="syn1m", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-sample", type=int, default=20_000)
+    ap.add_argument("--cpu-sample", type=int, default=100_000)
     ap.add_argument("--staged", action="store_true", help="one launch per block step instead of the persistent kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -1,0 +1,14 @@
+#!/bin/bash
+# bench + profiles on one B200
+mkdir -p gpurun_out
+timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench exit $?"
+tail -3 gpurun_out/bench_ours.err; cat gpurun_out/bench_ours.json
+timeout 900 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "ref exit $?"
+cat gpurun_out/bench_ref.json
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv \
+   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches exit $?"
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_round -s 8 -c 2 -o gpurun_out/prof_round \
+   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_round.log 2>&1; echo "ncu round exit $?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_ridge -s 6 -c 3 -o gpurun_out/prof_ridge \
+   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_ridge.log 2>&1; echo "ncu ridge exit $?"
+ls -la gpurun_out/
