@@ -236,7 +236,11 @@ def run_ours(args, w):
         comm = Comm(None)
         Y0 = comm.broadcast_array(Y0, 0)
     prob = make_problem(w, Z, codes, Pr_b, N_total, lo)
-    opts = {"persistent": 0} if args.staged else None
+    opts = {"persistent": 0} if args.staged else {}
+    for kv in args.engine_opt:
+        k, v = kv.split("=")
+        opts[k] = int(v)
+    opts = opts or None
     ho = Harmony(prob, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, SEED, local_rank, perm_mode="device",
                  comm=comm, engine_options=opts, run=False)
     eng = ho._engine
@@ -367,6 +371,7 @@ def main():
     ap.add_argument("--staged", action="store_true", help="one launch per block step instead of the persistent kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--engine-opt", action="append", default=[], help="name=int engine option (debug / A-B runs)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":

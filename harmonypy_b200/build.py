@@ -22,6 +22,7 @@ LIB = os.path.join(HERE, "libharmony_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 INSTANCES = [(k, j) for k in (1, 2, 4, 8) for j in (4, 8, 16)]
+MMA_INSTANCES = [(4, 1), (8, 1), (14, 1), (16, 1), (8, 2), (14, 2), (16, 2)]
 
 
 def _nvcc():
@@ -64,6 +65,9 @@ def build(force=False, jobs=None, verbose=True):
     for k, j in INSTANCES:
         work.append((os.path.join(CSRC, "hmy_inst.cu"), os.path.join(OBJ, f"hmy_inst_{k}_{j}.o"),
                      [f"-DHMY_KPT={k}", f"-DHMY_JPW={j}"]))
+    for nt, wn in MMA_INSTANCES:
+        work.append((os.path.join(CSRC, "hmy_inst_mma.cu"), os.path.join(OBJ, f"hmy_inst_mma_{nt}_{wn}.o"),
+                     [f"-DHMY_NT={nt}", f"-DHMY_WN={wn}"]))
     jobs = jobs or min(len(work), os.cpu_count() or 4)
     if verbose:
         print(f"[harmonypy_b200.build] compiling {len(work)} objects for sm_100a with {jobs} jobs", flush=True)

@@ -14,6 +14,7 @@
 #include "../../include/harmony_b200.h"
 #include "hmy_common.cuh"
 #include "hmy_round.cuh"
+#include "hmy_round_mma.cuh"
 #include "hmy_ridge.cuh"
 
 #define HMY_VERSION "harmony_b200 0.1.0 (sm_100a)"
@@ -29,6 +30,9 @@ struct hmy_ctx {
     std::string err;
     std::vector<int> levels, level_off;
     int KPT = 0, JPW = 0;
+    int WN = 1, round_threads = HMY_THREADS;
+    bool use_mma = false, want_mma = true;
+    int force_wn = 0;
     int G = 0, sms = 0;
     int smem_round = 0, smem_mom = 0, smem_apply = 0, smem_solve = 0;
     int grid_ridge = 0;
@@ -48,6 +52,7 @@ struct hmy_ctx {
     unsigned char* zero_round = nullptr; size_t zero_round_bytes = 0;
     unsigned char* zero_ridge = nullptr; size_t zero_ridge_bytes = 0;
     long long* d_perm = nullptr;
+    int* d_cnt = nullptr; int list_chunks = 0;
     float* d_tmp = nullptr; size_t tmp_bytes = 0;
     double* h_obj = nullptr;     // pinned
     // counters / timers
@@ -89,6 +94,31 @@ HMY_DECL_BIND(1, 4) HMY_DECL_BIND(1, 8) HMY_DECL_BIND(1, 16)
 HMY_DECL_BIND(2, 4) HMY_DECL_BIND(2, 8) HMY_DECL_BIND(2, 16)
 HMY_DECL_BIND(4, 4) HMY_DECL_BIND(4, 8) HMY_DECL_BIND(4, 16)
 HMY_DECL_BIND(8, 4) HMY_DECL_BIND(8, 8) HMY_DECL_BIND(8, 16)
+
+#define HMY_DECL_BIND_MMA(N_, W_) extern "C" void hmy_bind_mma_##N_##_##W_(const void** fns);
+HMY_DECL_BIND_MMA(4, 1) HMY_DECL_BIND_MMA(8, 1) HMY_DECL_BIND_MMA(14, 1) HMY_DECL_BIND_MMA(16, 1)
+HMY_DECL_BIND_MMA(8, 2) HMY_DECL_BIND_MMA(14, 2) HMY_DECL_BIND_MMA(16, 2)
+
+// tensor-core round kernels: d <= 64 and K <= 256 (everything else stays on the SIMT kernels)
+static bool bind_mma(hmy_ctx* ctx) {
+    const HmyDev& st = ctx->st;
+    if (st.d > 64 || st.K > 256) return false;
+    const int KT = (st.K + 7) / 8;
+    ctx->WN = (st.K <= 128) ? 1 : 2;
+    if (ctx->force_wn == 2 && KT >= 2) ctx->WN = 2;
+    const int ntw = (ctx->WN == 1) ? KT : (KT + 1) / 2;
+    const void* f[2] = {nullptr, nullptr};
+    if (ctx->WN == 1) {
+        if (ntw <= 4) hmy_bind_mma_4_1(f); else if (ntw <= 8) hmy_bind_mma_8_1(f);
+        else if (ntw <= 14) hmy_bind_mma_14_1(f); else hmy_bind_mma_16_1(f);
+    } else {
+        if (ntw <= 8) hmy_bind_mma_8_2(f); else if (ntw <= 14) hmy_bind_mma_14_2(f); else hmy_bind_mma_16_2(f);
+    }
+    ctx->fn_round = f[0]; ctx->fn_stage = f[1];
+    ctx->round_threads = 128 * ctx->WN;
+    ctx->use_mma = true;
+    return true;
+}
 
 static bool bind_for(hmy_ctx* ctx) {
     const void* f[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -223,22 +253,34 @@ static int plan_round(hmy_ctx* ctx) {
     if (nblk < 1 || nblk > HMY_MAX_NBLK) FAIL("block_size gives an unsupported number of blocks (1..250)");
     st.nblk = nblk;
     st.cpb = (long long)((double)st.Nglobal * (double)ctx->block_size);      // harmony.py:475
-    ctx->smem_round = round_smem_plan(st.dp, st.KS, st.B, st.V, nblk, ctx->JPW).total;
+    if (!bind_for(ctx)) FAIL("no kernel instantiation for this (K, d)");
+    ctx->use_mma = false; ctx->round_threads = HMY_THREADS;
+    if (ctx->want_mma) bind_mma(ctx);
+    ctx->smem_round = ctx->use_mma ? mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, nblk, ctx->WN).total
+                                   : round_smem_plan(st.dp, st.KS, st.B, st.V, nblk, ctx->JPW).total;
     if (ctx->smem_round > 227 * 1024) FAIL("round kernel needs more than 227 KB of shared memory for this (K, B, d, block_size)");
     CK(cudaFuncSetAttribute(ctx->fn_round, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
     CK(cudaFuncSetAttribute(ctx->fn_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
     int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, HMY_THREADS, ctx->smem_round));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, ctx->round_threads, ctx->smem_round));
     if (nb < 1) FAIL("round kernel does not fit on an SM");
     ctx->G = nb * ctx->sms;
     // per-round zero block: Told | Dnew | Yacc is separate (ridge also uses it) | obj
     const size_t nT = (size_t)nblk * st.B * st.K;
-    ctx->zero_round_bytes = 2 * nT * sizeof(float) + 4 * sizeof(double);
+    ctx->zero_round_bytes = 2 * nT * sizeof(float) + (4 + (size_t)st.B * st.K) * sizeof(double);
     ctx->zero_round_bytes = (ctx->zero_round_bytes + 7) & ~(size_t)7;
     if (dev_alloc(ctx, &ctx->zero_round, ctx->zero_round_bytes + 8)) return 1;
     st.obj = (double*)ctx->zero_round;                      // 8-byte aligned at the front
-    st.Told = (float*)(st.obj + 4); st.Dnew = st.Told + nT;
-    if (dev_alloc(ctx, &st.list_off, (size_t)ctx->G * (nblk + 1))) return 1;
+    st.Ofresh = st.obj + 4;
+    st.Told = (float*)(st.Ofresh + (size_t)st.B * st.K); st.Dnew = st.Told + nT;
+    if (dev_alloc(ctx, &st.blk_start, (size_t)nblk + 1)) return 1;
+    ctx->list_chunks = 4 * ctx->sms;
+    {
+        const size_t sm = ((size_t)nblk * HMY_LIST_THREADS + nblk) * sizeof(unsigned int);
+        if (sm > 200 * 1024) FAIL("block_size gives too many blocks for the list builder");
+        CK(cudaFuncSetAttribute((const void*)k_block_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    }
+    if (dev_alloc(ctx, &ctx->d_cnt, (size_t)ctx->list_chunks * nblk)) return 1;
     int nbr = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbr, ctx->fn_apply, HMY_THREADS, ctx->smem_apply));
     ctx->grid_ridge = std::max(1, nbr) * ctx->sms;
@@ -397,7 +439,7 @@ static int staged_tables(hmy_ctx* ctx, int what, int blk) {
 static int staged_round(hmy_ctx* ctx, int what, int blk) {
     HmyDev st = ctx->st;
     void* args[] = {&st, &what, &blk};
-    return launch(ctx, ctx->fn_stage, dim3(ctx->G), dim3(HMY_THREADS), args, ctx->smem_round, false);
+    return launch(ctx, ctx->fn_stage, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, false);
 }
 
 // ---- a2: init ------------------------------------------------------------------------------
@@ -421,13 +463,12 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
     if (ctx->persistent && !ctx->ar) {
         HmyDev s = st; int mode = 1; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(HMY_THREADS), args, ctx->smem_round, true)) return 1;
+        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
         ctx->gen += 1;
     } else {
         if (staged_round(ctx, 2, 0)) return 1;
-        if (allreduce(ctx, st.Dnew, (int64_t)st.B * st.K, 0)) return 1;
+        if (allreduce(ctx, st.obj, 4 + (int64_t)st.B * st.K, 1)) return 1;     // objective sums | Ofresh
         if (allreduce(ctx, st.Yacc, (int64_t)st.K * st.dp, 1)) return 1;
-        if (allreduce(ctx, st.obj, 4, 1)) return 1;
         if (staged_tables(ctx, 2, 1)) return 1;
     }
     if (timer_end(ctx, ctx->ev_init)) return 1;
@@ -454,13 +495,21 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
     ctx->launches++;
     CK(cudaGetLastError());
     ctx->round_counter++;
+    {   // per-block cell lists (stable counting sort over position chunks)
+        const size_t sm = ((size_t)st.nblk * HMY_LIST_THREADS + st.nblk) * sizeof(unsigned int);
+        k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(st, ctx->d_cnt, 1);
+        k_block_scan<<<1, 256, 0, ctx->stream>>>(st, ctx->d_cnt, ctx->list_chunks);
+        k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(st, ctx->d_cnt, 0);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+    }
     CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
     CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
     if (timer_begin(ctx, ctx->ev_round)) return 1;
     if (ctx->persistent && !ctx->ar) {
         HmyDev s = st; int mode = 0; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(HMY_THREADS), args, ctx->smem_round, true)) return 1;
+        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
         ctx->gen += (unsigned int)st.nblk + 1u;
     } else {
         const int64_t nT = (int64_t)st.nblk * st.B * st.K, BK = (int64_t)st.B * st.K;
@@ -473,7 +522,7 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
             if (blk + 1 < st.nblk && staged_tables(ctx, 1, blk + 1)) return 1;
         }
         if (allreduce(ctx, st.Yacc, (int64_t)st.K * st.dp, 1)) return 1;
-        if (allreduce(ctx, st.obj, 4, 1)) return 1;
+        if (allreduce(ctx, st.obj, 4 + (int64_t)st.B * st.K, 1)) return 1;     // objective sums | Ofresh
         if (staged_tables(ctx, 2, 0)) return 1;
     }
     if (timer_end(ctx, ctx->ev_round)) return 1;
@@ -575,6 +624,14 @@ extern "C" int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes) {
             }
             return 0;
         }
+        case 9: {   // HMY_TRACE: uint64 [grid][HMY_TRACE_SLOTS] globaltimer stamps of the last round
+            const size_t n = (size_t)(ctx->G + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long);
+            if (!st.trace) FAIL("hmy_get(trace): tracing is off");
+            if ((size_t)bytes != n) FAIL("hmy_get(trace): wrong buffer size");
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaMemcpy(host_out, st.trace, n, cudaMemcpyDeviceToHost));
+            return 0;
+        }
         case HMY_W: {
             const size_t n = (size_t)st.B * st.K * st.d;
             if ((size_t)bytes != n * sizeof(float)) FAIL("hmy_get(W): wrong buffer size");
@@ -600,6 +657,24 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
     if (n == "persistent") { ctx->persistent = value != 0; return 0; }
     if (n == "seed") { ctx->seed = (unsigned long long)value * 0x9E3779B97F4A7C15ull + 0x243F6A8885A308D3ull; ctx->round_counter = 0; return 0; }
     if (n == "timing") { ctx->timing = value != 0; return 0; }
+    if (n == "trace") {
+        // per-CTA timeline of the persistent round kernel (debug / profiling aid)
+        CK(cudaSetDevice(ctx->device));
+        if (value && !ctx->st.trace) {
+            if (!ctx->have_params) FAIL("trace: set params first");
+            if (dev_alloc(ctx, &ctx->st.trace, (size_t)(ctx->G + 1) * HMY_TRACE_SLOTS)) return 1;
+            CK(cudaMemset(ctx->st.trace, 0, (size_t)(ctx->G + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long)));
+        }
+        return 0;
+    }
+    if (n == "mma_wn") {
+        if (ctx->have_params) FAIL("option mma_wn must be set before hmy_set_params");
+        ctx->force_wn = (int)value; return 0;
+    }
+    if (n == "mma") {
+        if (ctx->have_params) FAIL("option mma must be set before hmy_set_params");
+        ctx->want_mma = value != 0; return 0;
+    }
     if (n == "reset") {
         // back to the freshly-uploaded state (benchmark steps restart from here)
         CK(cudaSetDevice(ctx->device));
@@ -623,6 +698,8 @@ extern "C" int64_t hmy_counter(const hmy_ctx* ctx, const char* name) {
     if (n == "smem_round") return ctx->smem_round;
     if (n == "nblk") return ctx->st.nblk;
     if (n == "ncombo") return ctx->st.ncombo;
+    if (n == "mma") return ctx->use_mma ? 1 : 0;
+    if (n == "round_threads") return ctx->round_threads;
     return -1;
 }
 

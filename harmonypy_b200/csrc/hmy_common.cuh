@@ -21,6 +21,7 @@
 #define HMY_CPW 8            // cells per warp inside a tile (HMY_TILE / HMY_WARPS)
 #define HMY_MAX_V 8
 #define HMY_MAX_NBLK 250
+#define HMY_TRACE_SLOTS 128
 
 struct HmyDev {
     long long N;             // cells on this rank
@@ -39,12 +40,13 @@ struct HmyDev {
     int* order;              // order[pos] = caller's local index of the cell stored at pos
     int* pos_of;             // inverse of order
     unsigned char* blk;
-    int* list; int* list_off;            // per-CTA block lists, list_off[G][nblk+1]
+    int* list; long long* blk_start;     // cells of block b: list[blk_start[b] .. blk_start[b+1]) (ascending positions)
     int* seg;                            // ridge work items: [nseg][3] = start, count, combo
     // tables
     float* Yhat; float* Ynext; double* Yacc;   // Yhat: centroids this stage reads; Ynext: the ones it produces
     float* Told; float* Dnew; float* P;
     double* O; double* Orun;             // [B][K]
+    double* Ofresh;                      // [B][K] sum over the round's blocks of the re-added batch sums = the new O
     double* obj;                         // [0..2] objective sums, [3] spare
     double* obj_out;                     // [3] finished objective of the last stage
     float* Pr_b; float* theta; float* sigma; float* lamb;   // lamb[B+1]
@@ -53,7 +55,17 @@ struct HmyDev {
     float* W;                // [B][K][dp]
     // grid barrier
     unsigned int* bar_count; unsigned int* bar_gen;
+    // optional per-CTA timeline (globaltimer ns), [grid][HMY_TRACE_SLOTS]; nullptr = off
+    unsigned long long* trace;
 };
+
+__device__ __forceinline__ void hmy_trace(const HmyDev& st, int slot) {
+    if (st.trace != nullptr && threadIdx.x == 0 && slot < HMY_TRACE_SLOTS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + slot] = t;
+    }
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -80,30 +92,59 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
 // Grid-wide barrier with a serial section: every CTA arrives; the LAST one to arrive runs
 // `serial()` (all of its threads) and then releases generation `gen`; the others wait.
 // Requires all CTAs of the grid to be co-resident (cooperative launch).
+// Memory ordering follows the cooperative-groups grid.sync() pattern: bar.sync makes the
+// CTA's prior writes (incl. its REDs) happen-before thread 0's gpu-scope fence, which is
+// cumulative; the ticket atomic / the release store then publish them.
 template <class F>
 __device__ __forceinline__ void grid_barrier_serial(const HmyDev& st, unsigned int nctas,
                                                     unsigned int gen, int* s_flag, F serial) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence();
         unsigned int t = atomicAdd(st.bar_count, 1u);
         *s_flag = (t == nctas - 1u);
     }
     __syncthreads();
     if (*s_flag) {
-        __threadfence();
+#define HMY_SER_STAMP(i_)                                                                        \
+        if (st.trace != nullptr && threadIdx.x == 0) {                                             \
+            unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));          \
+            st.trace[(size_t)nctas * HMY_TRACE_SLOTS + 4 * (gen & 31u) + (i_)] = t_;               \
+        }
+        HMY_SER_STAMP(0)
+        __threadfence();                 // acquire side: see every other CTA's contributions
+        HMY_SER_STAMP(1)
         serial();
-        __threadfence();
         __syncthreads();
+        HMY_SER_STAMP(2)
         if (threadIdx.x == 0) {
             *st.bar_count = 0u;
             __threadfence();
+            HMY_SER_STAMP(3)
             st_release_u32(st.bar_gen, gen);
         }
     } else {
         if (threadIdx.x == 0) {
             while ((int)(ld_acquire_u32(st.bar_gen) - gen) < 0) { __nanosleep(20); }
         }
+    }
+    __syncthreads();
+}
+
+// Plain grid barrier (no serial section).
+__device__ __forceinline__ void grid_barrier(const HmyDev& st, unsigned int nctas, unsigned int gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int t = atomicAdd(st.bar_count, 1u);
+        if (t == nctas - 1u) {
+            *st.bar_count = 0u;
+            __threadfence();
+            st_release_u32(st.bar_gen, gen);
+        } else {
+            while ((int)(ld_acquire_u32(st.bar_gen) - gen) < 0) { __nanosleep(20); }
+        }
+        __threadfence();
     }
     __syncthreads();
 }

@@ -15,6 +15,8 @@
 
 // ------------------------------------------------------------------------------------------
 // shared-memory plan (identical on host and device)
+__host__ __device__ inline int phase0_tables(int KS) { return (KS <= 128) ? 4 : 2; }
+
 struct RoundSmem {
     int ZS, RS;
     int off_YsT, off_sigma, off_Ps, off_union, off_misc;
@@ -39,9 +41,8 @@ __host__ __device__ inline RoundSmem round_smem_plan(int dp, int KS, int B, int 
     s.off_ccombo = a; a += HMY_TILE * 4;
     s.off_clev = a;   a += HMY_TILE * V * 4;
     int b = o;
-    s.off_T = b;      b += 4 * nblk * KS * 4;
-    s.off_cnt = b;    b += nblk * HMY_THREADS * 4;
-    s.off_btot = b;   b += (nblk + 1) * 4;
+    s.off_T = b;      b += phase0_tables(KS) * nblk * KS * 4;
+    s.off_cnt = b;    s.off_btot = b;
     o = (a > b ? a : b);
     o = (o + 15) & ~15;
     s.off_misc = o;   o += 8 * 256 + 128;      // K doubles of scratch for the serial sections
@@ -73,23 +74,80 @@ __device__ inline void serial_rowsum(const HmyDev& st, const double* Otab, doubl
 
 // Put block blk-1 back (harmony.py:506-507), take block blk out (:491-492), then the penalty
 // (E / (O + E))^theta with the reference's clamps (:495-499, :579-584).
-__device__ inline void serial_prepare_block(const HmyDev& st, int blk, double* s_row) {
-    const int BK = st.B * st.K;
-    for (int i = threadIdx.x; i < BK; i += blockDim.x) {
-        double o = __ldcg(&st.Orun[i]);
-        if (blk > 0) o += (double)__ldcg(&st.Dnew[(size_t)(blk - 1) * BK + i]);
-        o -= (double)__ldcg(&st.Told[(size_t)blk * BK + i]);
-        __stcg(&st.Orun[i], o);
-    }
-    __syncthreads();
-    serial_rowsum(st, st.Orun, s_row);
-    for (int i = threadIdx.x; i < BK; i += blockDim.x) {
-        const int b = i / st.K, k = i - b * st.K;
-        const float o = (float)__ldcg(&st.Orun[i]);
-        const float e = (float)(s_row[k] * (double)st.Pr_b[b]);
-        const float den = fmaxf(o + e, 1e-8f);
-        const float ratio = fminf(fmaxf(e / den, 1e-8f), 1.0f);
-        __stcg(&st.P[i], powf(ratio, st.theta[b]));
+// Thread k owns cluster k and issues ALL loads of its column before using any of them: this
+// runs on one CTA between two blocks, so its latency sits on every block's critical path.
+#define HMY_SER_B 24
+__device__ inline void serial_prepare_block(const HmyDev& st, int blk, double* /*s_row*/) {
+    const int BK = st.B * st.K, K = st.K, B = st.B;
+    const float* dn = st.Dnew + (size_t)(blk > 0 ? blk - 1 : 0) * BK;
+    const float* to = st.Told + (size_t)blk * BK;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double rs = 0.0;
+        if (B <= HMY_SER_B) {
+            double o[HMY_SER_B]; float a[HMY_SER_B], r[HMY_SER_B], pr[HMY_SER_B], th[HMY_SER_B];
+#pragma unroll
+            for (int b = 0; b < HMY_SER_B; ++b) {
+                pr[b] = (b < B) ? st.Pr_b[b] : 0.f;
+                th[b] = (b < B) ? st.theta[b] : 2.f;
+                o[b] = (b < B) ? __ldcg(&st.Orun[b * K + k]) : 0.0;
+                a[b] = (b < B && blk > 0) ? __ldcg(&dn[b * K + k]) : 0.f;
+                r[b] = (b < B) ? __ldcg(&to[b * K + k]) : 0.f;
+            }
+#pragma unroll
+            for (int b = 0; b < HMY_SER_B; ++b) {
+                o[b] += (double)a[b] - (double)r[b];
+                if (b < st.lev0) rs += o[b];
+            }
+#pragma unroll
+            for (int b = 0; b < HMY_SER_B; ++b) {
+                if (b < B) {
+                    __stcg(&st.Orun[b * K + k], o[b]);
+                    const float of = (float)o[b];
+                    const float e = (float)(rs * (double)pr[b]);
+                    const float ratio = fminf(fmaxf(e / fmaxf(of + e, 1e-8f), 1e-8f), 1.0f);
+                    __stcg(&st.P[b * K + k], (th[b] == 2.0f) ? ratio * ratio : powf(ratio, th[b]));
+                }
+            }
+        } else {
+            for (int b0 = 0; b0 < B; b0 += 8) {
+                double o[8]; float a[8], r[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + u;
+                    o[u] = (b < B) ? __ldcg(&st.Orun[b * K + k]) : 0.0;
+                    a[u] = (b < B && blk > 0) ? __ldcg(&dn[b * K + k]) : 0.f;
+                    r[u] = (b < B) ? __ldcg(&to[b * K + k]) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + u;
+                    if (b < B) {
+                        const double v = o[u] + (double)a[u] - (double)r[u];
+                        __stcg(&st.Orun[b * K + k], v);
+                        if (b < st.lev0) rs += v;
+                    }
+                }
+            }
+            for (int b0 = 0; b0 < B; b0 += 8) {
+                double o[8]; float pr[8], th[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    o[u] = (b0 + u < B) ? __ldcg(&st.Orun[(b0 + u) * K + k]) : 0.0;
+                    pr[u] = (b0 + u < B) ? st.Pr_b[b0 + u] : 0.f;
+                    th[u] = (b0 + u < B) ? st.theta[b0 + u] : 2.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int b = b0 + u;
+                    if (b < B) {
+                        const float of = (float)o[u];
+                        const float e = (float)(rs * (double)pr[u]);
+                        const float ratio = fminf(fmaxf(e / fmaxf(of + e, 1e-8f), 1e-8f), 1.0f);
+                        __stcg(&st.P[b * K + k], (th[u] == 2.0f) ? ratio * ratio : powf(ratio, th[u]));
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
 }
@@ -101,10 +159,10 @@ __device__ inline void serial_prepare_block(const HmyDev& st, int blk, double* s
 __device__ inline void serial_finalize(const HmyDev& st, int mode, double* s_row, double* s_red) {
     const int BK = st.B * st.K;
     if (mode != 2) {
-        const int last = (mode == 1) ? 0 : st.nblk - 1;
+        // the maintained O after a full pass over the blocks is the sum of what the blocks put
+        // back (harmony.py:506-507 over all blocks; for init: harmony.py:389)
         for (int i = threadIdx.x; i < BK; i += blockDim.x) {
-            double o = (mode == 1) ? 0.0 : __ldcg(&st.Orun[i]);
-            o += (double)__ldcg(&st.Dnew[(size_t)last * BK + i]);
+            const double o = __ldcg(&st.Ofresh[i]);
             __stcg(&st.Orun[i], o);
             __stcg(&st.O[i], o);
         }
@@ -141,6 +199,14 @@ __device__ inline void serial_finalize(const HmyDev& st, int mode, double* s_row
             st.Ynext[(size_t)k * st.dp + j] = (j < st.d) ? (float)(__ldcg(&st.Yacc[(size_t)k * st.dp + j]) * inv) : 0.f;
     }
     __syncthreads();
+}
+
+// CTA `cta` of `G` takes an equal share of block blk's cell list (global, position-sorted)
+__device__ __forceinline__ void block_share(const HmyDev& st, int blk, unsigned int cta, unsigned int G,
+                                            long long& lb, long long& le) {
+    const long long b0 = st.blk_start[blk], n = st.blk_start[blk + 1] - b0;
+    lb = b0 + n * cta / G;
+    le = b0 + n * (cta + 1) / G;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -193,55 +259,22 @@ __device__ __forceinline__ void zero_step_buffers(RoundCtx<KPT, JPW>& c) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase 0: bucket the CTA's cells by block (stable counting sort -> list/list_off) and sum
-// what each block will remove: Told[blk][b][k] = sum_{n in blk, level b} R_old[n][k]
+// Phase 0: sum what each block will remove: Told[blk][b][k] = sum_{n in blk, level b} R_old[n][k]
 // (the R_block @ Phi_block.T and R_block.sum of harmony.py:491-492, for all blocks at once).
-template <int KPT, int JPW>
-__device__ void phase0(RoundCtx<KPT, JPW>& c, const HmyDev& st, long long c0, long long c1) {
+struct Phase0Mem { float* T; unsigned int* cnt; int* btot; int KS; };
+
+template <int NTHR>
+__device__ void phase0(const Phase0Mem c, const HmyDev& st, long long c0, long long c1) {
+    constexpr int HMY_THREADS_L = NTHR;
     const int tid = threadIdx.x;
     const int n = (int)(c1 - c0);
     const int nblk = st.nblk;
-    // ---- (a) counting sort by block, deterministic (ascending cell order inside a block)
-    const int per = (n + HMY_THREADS - 1) / HMY_THREADS;
-    const int t0 = min(n, tid * per), t1 = min(n, t0 + per);
-    for (int i = tid; i < nblk * HMY_THREADS; i += HMY_THREADS) c.cnt[i] = 0u;
-    __syncthreads();
-    for (int i = t0; i < t1; ++i) c.cnt[(int)st.blk[c0 + i] * HMY_THREADS + tid]++;
-    __syncthreads();
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        for (int b = warp; b < nblk; b += HMY_WARPS) {
-            unsigned int loc[8]; unsigned int s = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { loc[i] = c.cnt[b * HMY_THREADS + 8 * lane + i]; s += loc[i]; }
-            unsigned int inc = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            unsigned int run = inc - s;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { c.cnt[b * HMY_THREADS + 8 * lane + i] = run; run += loc[i]; }
-            if (lane == 31) c.btot[b] = (int)inc;
-        }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        int run = 0;
-        int* lo = st.list_off + (size_t)blockIdx.x * (nblk + 1);
-        for (int b = 0; b < nblk; ++b) { const int t = c.btot[b]; c.btot[b] = run; lo[b] = run; run += t; }
-        lo[nblk] = run;
-    }
-    __syncthreads();
-    for (int i = t0; i < t1; ++i) {
-        const int b = st.blk[c0 + i];
-        const unsigned int pos = (unsigned int)c.btot[b] + c.cnt[b * HMY_THREADS + tid]++;
-        st.list[c0 + pos] = (int)(c0 + i);
-    }
-    __syncthreads();
     // ---- (b) Told.  GS threads cover one R row; NG groups x U tables keep the shared-memory
     // read-modify-write chains of consecutive cells independent.
     const int GS = (c.KS <= 128) ? 128 : 256;
-    const int NG = HMY_THREADS / GS;
-    const int U = 4 / NG;
+    const int NG = HMY_THREADS_L / GS;
+    const int NTAB = phase0_tables(c.KS);
+    const int U = NTAB / NG;
     const int g = tid / GS, kk = tid - g * GS;
     const bool active = kk < st.K;
     const int TS = nblk * c.KS;                 // one table
@@ -249,7 +282,7 @@ __device__ void phase0(RoundCtx<KPT, JPW>& c, const HmyDev& st, long long c0, lo
     while (s0 < c1) {
         const int combo = st.combo[s0];
         const long long s1 = min(c1, st.combo_start[combo + 1]);
-        for (int i = tid; i < 4 * TS; i += HMY_THREADS) c.T[i] = 0.f;
+        for (int i = tid; i < NTAB * TS; i += HMY_THREADS_L) c.T[i] = 0.f;
         __syncthreads();
         if (kk < c.KS) {
             float* Tg = c.T + (size_t)g * U * TS + kk;
@@ -283,9 +316,10 @@ __device__ void phase0(RoundCtx<KPT, JPW>& c, const HmyDev& st, long long c0, lo
             }
         }
         __syncthreads();
-        for (int i = tid; i < nblk * st.K; i += HMY_THREADS) {
+        for (int i = tid; i < nblk * st.K; i += HMY_THREADS_L) {
             const int b = i / st.K, k = i - b * st.K;
-            const float s = c.T[b * c.KS + k] + c.T[TS + b * c.KS + k] + c.T[2 * TS + b * c.KS + k] + c.T[3 * TS + b * c.KS + k];
+            float s = 0.f;
+            for (int u = 0; u < NTAB; ++u) s += c.T[u * TS + b * c.KS + k];
             if (s != 0.f) {
                 for (int v = 0; v < st.V; ++v) {
                     const int lev = st.combo_lev[combo * st.V + v];
@@ -306,6 +340,7 @@ __device__ __forceinline__ void flush_run(RoundCtx<KPT, JPW>& c, const HmyDev& s
         for (int v = 0; v < st.V; ++v) {
             const int lev = st.combo_lev[c.run_combo * st.V + v];
             atomicAdd(&st.Dnew[((size_t)blk * st.B + lev) * st.K + threadIdx.x], c.run_sum);
+            atomicAdd(&st.Ofresh[(size_t)lev * st.K + threadIdx.x], (double)c.run_sum);
         }
     }
     c.run_combo = -1; c.run_sum = 0.f;
@@ -480,18 +515,19 @@ __global__ void __launch_bounds__(HMY_THREADS) k_round(HmyDev st, int mode, unsi
         grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() { serial_finalize(st, 1, c.sRow, c.sRed); });
         return;
     }
-    phase0(c, st, c0, c1);
+    phase0<HMY_THREADS>(Phase0Mem{c.T, c.cnt, c.btot, c.KS}, st, c0, c1);
     unsigned int gen = gen_base + 1u;
     grid_barrier_serial(st, G, gen++, c.sFlag, [&]() { serial_copy_O(st); serial_prepare_block(st, 0, c.sRow); });
     zero_step_buffers(c);
-    const int* lo = st.list_off + (size_t)blockIdx.x * (st.nblk + 1);
     for (int blk = 0; blk < st.nblk; ++blk) {
         for (int i = threadIdx.x; i < st.B * c.KS; i += HMY_THREADS) {
             const int b = i / c.KS, k = i - b * c.KS;
             c.Ps[i] = (k < st.K) ? __ldcg(&st.P[b * st.K + k]) : 0.f;
         }
         __syncthreads();
-        process_block(c, st, blk, st.list, c0 + lo[blk], c0 + lo[blk + 1], false);
+        long long lb, le;
+        block_share(st, blk, blockIdx.x, G, lb, le);
+        process_block(c, st, blk, st.list, lb, le, false);
         if (blk + 1 < st.nblk) {
             grid_barrier_serial(st, G, gen++, c.sFlag, [&]() { serial_prepare_block(st, blk + 1, c.sRow); });
         } else {
@@ -511,7 +547,7 @@ __global__ void __launch_bounds__(HMY_THREADS) k_round_stage(HmyDev st, int what
     round_ctx_init(c, st, smem);
     const unsigned int G = gridDim.x;
     const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G;
-    if (what == 0) { phase0(c, st, c0, c1); return; }
+    if (what == 0) { phase0<HMY_THREADS>(Phase0Mem{c.T, c.cnt, c.btot, c.KS}, st, c0, c1); return; }
     load_centroids(c, st);
     zero_step_buffers(c);
     if (what == 1) {
@@ -522,8 +558,9 @@ __global__ void __launch_bounds__(HMY_THREADS) k_round_stage(HmyDev st, int what
     }
     __syncthreads();
     if (what == 1) {
-        const int* lo = st.list_off + (size_t)blockIdx.x * (st.nblk + 1);
-        process_block(c, st, blk, st.list, c0 + lo[blk], c0 + lo[blk + 1], false);
+        long long lb, le;
+        block_share(st, blk, blockIdx.x, G, lb, le);
+        process_block(c, st, blk, st.list, lb, le, false);
     } else {
         process_block(c, st, 0, nullptr, c0, c1, true);
     }
@@ -531,6 +568,65 @@ __global__ void __launch_bounds__(HMY_THREADS) k_round_stage(HmyDev st, int what
 }
 
 #ifdef HMY_NONTEMPLATE_KERNELS
+// ------------------------------------------------------------------------------------------
+// Per-block cell lists of the round: list[blk_start[b] .. blk_start[b+1]) = positions of the
+// cells of block b, ascending (stable counting sort over chunks of the position range).
+#define HMY_LIST_THREADS 256
+// pass 1 (count = 1): cnt[chunk][b]; pass 2 (count = 0): scatter using base[chunk][b]
+__global__ void __launch_bounds__(HMY_LIST_THREADS) k_block_lists(HmyDev st, int* cnt, int count) {
+    extern __shared__ unsigned int s_cnt[];            // [nblk][256] + [nblk]
+    const int tid = threadIdx.x, nblk = st.nblk;
+    unsigned int* s_tot = s_cnt + nblk * HMY_LIST_THREADS;
+    const long long c0 = (long long)blockIdx.x * st.N / gridDim.x, c1 = (long long)(blockIdx.x + 1) * st.N / gridDim.x;
+    const int n = (int)(c1 - c0);
+    const int per = (n + HMY_LIST_THREADS - 1) / HMY_LIST_THREADS;
+    const int t0 = min(n, tid * per), t1 = min(n, t0 + per);
+    for (int i = tid; i < nblk * HMY_LIST_THREADS; i += HMY_LIST_THREADS) s_cnt[i] = 0u;
+    __syncthreads();
+    for (int i = t0; i < t1; ++i) s_cnt[(int)st.blk[c0 + i] * HMY_LIST_THREADS + tid]++;
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int b = warp; b < nblk; b += HMY_LIST_THREADS / 32) {
+        unsigned int loc[8]; unsigned int s = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { loc[i] = s_cnt[b * HMY_LIST_THREADS + 8 * lane + i]; s += loc[i]; }
+        unsigned int inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        unsigned int run = inc - s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { s_cnt[b * HMY_LIST_THREADS + 8 * lane + i] = run; run += loc[i]; }
+        if (lane == 31) s_tot[b] = inc;
+    }
+    __syncthreads();
+    if (count) {
+        for (int b = tid; b < nblk; b += HMY_LIST_THREADS) cnt[(size_t)blockIdx.x * nblk + b] = (int)s_tot[b];
+        return;
+    }
+    for (int i = t0; i < t1; ++i) {
+        const int b = st.blk[c0 + i];
+        const long long pos = st.blk_start[b] + cnt[(size_t)blockIdx.x * nblk + b] + s_cnt[b * HMY_LIST_THREADS + tid]++;
+        st.list[pos] = (int)(c0 + i);
+    }
+}
+
+// cnt[chunk][b] -> exclusive prefix over chunks (in place) and blk_start[b] (exclusive over blocks)
+__global__ void k_block_scan(HmyDev st, int* cnt, int nchunk) {
+    __shared__ long long tot[HMY_MAX_NBLK + 1];
+    const int nblk = st.nblk;
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
+        int run = 0;
+        for (int c = 0; c < nchunk; ++c) { const int v = cnt[(size_t)c * nblk + b]; cnt[(size_t)c * nblk + b] = run; run += v; }
+        tot[b] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        for (int b = 0; b < nblk; ++b) { st.blk_start[b] = run; run += tot[b]; }
+        st.blk_start[nblk] = run;
+    }
+}
+
 // single-CTA table kernel for staged mode: what 0 = copy O + prepare block 0,
 // 1 = prepare block `blk`, 2 = finalize (mode in `blk`)
 __global__ void __launch_bounds__(HMY_THREADS) k_tables(HmyDev st, int what, int blk) {

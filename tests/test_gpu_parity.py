@@ -95,6 +95,18 @@ def test_staged_launches_match_persistent_kernel():
     assert rel_max(a.R, b.R) < 2e-5
 
 
+def test_tensor_core_round_matches_simt_round():
+    """The fp16-split mma.sync kernels against the fp32 SIMT kernels (engine option mma=0)."""
+    inp, _ = load_case("synth")
+    a, _ = _engine_run(inp, options={"mma": 1}, record=False)
+    b, _ = _engine_run(inp, options={"mma": 0}, record=False)
+    assert a._engine.counter("mma") == 1 and b._engine.counter("mma") == 0
+    assert a.kmeans_rounds == b.kmeans_rounds
+    assert rel_max(a.Z_corr, b.Z_corr) < 1e-5
+    assert rel_max(a.R, b.R) < 1e-4
+    np.testing.assert_allclose(a.objective_kmeans, b.objective_kmeans, rtol=2e-6)
+
+
 def _oracle_for(prob, dtype=np.float64, **kw):
     from oracle.harmony_oracle import HarmonyOracle, onehot_from_codes
     return HarmonyOracle(prob.Z.T, onehot_from_codes(prob.codes, prob.levels, dtype), prob.Pr_b, prob.sigma,
