@@ -30,7 +30,7 @@ struct hmy_ctx {
     std::string err;
     std::vector<int> levels, level_off;
     int KPT = 0, JPW = 0;
-    int WN = 1, round_threads = HMY_THREADS;
+    int WN = 1, NT = 0, round_threads = HMY_THREADS;
     bool use_mma = false, want_mma = true;
     int force_wn = 0;
     int G = 0, sms = 0;
@@ -109,10 +109,11 @@ static bool bind_mma(hmy_ctx* ctx) {
     const int ntw = (ctx->WN == 1) ? KT : (KT + 1) / 2;
     const void* f[2] = {nullptr, nullptr};
     if (ctx->WN == 1) {
-        if (ntw <= 4) hmy_bind_mma_4_1(f); else if (ntw <= 8) hmy_bind_mma_8_1(f);
-        else if (ntw <= 14) hmy_bind_mma_14_1(f); else hmy_bind_mma_16_1(f);
+        if (ntw <= 4) { hmy_bind_mma_4_1(f); ctx->NT = 4; } else if (ntw <= 8) { hmy_bind_mma_8_1(f); ctx->NT = 8; }
+        else if (ntw <= 14) { hmy_bind_mma_14_1(f); ctx->NT = 14; } else { hmy_bind_mma_16_1(f); ctx->NT = 16; }
     } else {
-        if (ntw <= 8) hmy_bind_mma_8_2(f); else if (ntw <= 14) hmy_bind_mma_14_2(f); else hmy_bind_mma_16_2(f);
+        if (ntw <= 8) { hmy_bind_mma_8_2(f); ctx->NT = 8; } else if (ntw <= 14) { hmy_bind_mma_14_2(f); ctx->NT = 14; }
+        else { hmy_bind_mma_16_2(f); ctx->NT = 16; }
     }
     ctx->fn_round = f[0]; ctx->fn_stage = f[1];
     ctx->round_threads = 128 * ctx->WN;
@@ -256,7 +257,7 @@ static int plan_round(hmy_ctx* ctx) {
     if (!bind_for(ctx)) FAIL("no kernel instantiation for this (K, d)");
     ctx->use_mma = false; ctx->round_threads = HMY_THREADS;
     if (ctx->want_mma) bind_mma(ctx);
-    ctx->smem_round = ctx->use_mma ? mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, nblk, ctx->WN).total
+    ctx->smem_round = ctx->use_mma ? mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, nblk, ctx->WN, ctx->NT).total
                                    : round_smem_plan(st.dp, st.KS, st.B, st.V, nblk, ctx->JPW).total;
     if (ctx->smem_round > 227 * 1024) FAIL("round kernel needs more than 227 KB of shared memory for this (K, B, d, block_size)");
     CK(cudaFuncSetAttribute(ctx->fn_round, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));

@@ -169,12 +169,21 @@ __device__ inline void serial_finalize(const HmyDev& st, int mode, double* s_row
         __syncthreads();
         serial_rowsum(st, st.Orun, s_row);
         double part = 0.0;
-        for (int i = threadIdx.x; i < BK; i += blockDim.x) {
-            const int b = i / st.K, k = i - b * st.K;
-            const double o = __ldcg(&st.Orun[i]);
-            const float oc = fmaxf((float)o, 1e-8f);
-            const float ec = fmaxf((float)(s_row[k] * (double)st.Pr_b[b]), 1e-8f);
-            part += (double)st.sigma[k] * (double)st.theta[b] * (double)logf((oc + ec) / ec) * o;
+        for (int i0 = threadIdx.x; i0 < BK; i0 += blockDim.x * 8) {
+            double o8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; o8[u] = (i < BK) ? __ldcg(&st.Orun[i]) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + u * blockDim.x;
+                if (i < BK) {
+                    const int b = i / st.K, k = i - b * st.K;
+                    const double o = o8[u];
+                    const float oc = fmaxf((float)o, 1e-8f);
+                    const float ec = fmaxf((float)(s_row[k] * (double)st.Pr_b[b]), 1e-8f);
+                    part += (double)st.sigma[k] * (double)st.theta[b] * (double)logf((oc + ec) / ec) * o;
+                }
+            }
         }
         part = warp_sum_d(part);
         if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
@@ -188,15 +197,31 @@ __device__ inline void serial_finalize(const HmyDev& st, int mode, double* s_row
         }
         __syncthreads();
     }
-    // unit centroids from the accumulated sums
+    // unit centroids from the accumulated sums (each warp: 4 clusters at a time, loads up front)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int k = warp; k < st.K; k += nw) {
-        double ss = 0.0;
-        for (int j = lane; j < st.d; j += 32) { const double y = __ldcg(&st.Yacc[(size_t)k * st.dp + j]); ss += y * y; }
-        ss = warp_sum_d(ss);
-        const double inv = 1.0 / sqrt(ss);
-        for (int j = lane; j < st.dp; j += 32)
-            st.Ynext[(size_t)k * st.dp + j] = (j < st.d) ? (float)(__ldcg(&st.Yacc[(size_t)k * st.dp + j]) * inv) : 0.f;
+    for (int k0 = 4 * warp; k0 < st.K; k0 += 4 * nw) {
+        double y[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int k = k0 + q, j = lane + 32 * m;
+                y[q][m] = (k < st.K && j < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + j]) : 0.0;
+            }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = k0 + q;
+            double ss = y[q][0] * y[q][0] + y[q][1] * y[q][1] + y[q][2] * y[q][2] + y[q][3] * y[q][3];
+            ss = warp_sum_d(ss);
+            const double inv = 1.0 / sqrt(ss);
+            if (k < st.K) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int j = lane + 32 * m;
+                    if (j < st.dp) st.Ynext[(size_t)k * st.dp + j] = (j < st.d) ? (float)(y[q][m] * inv) : 0.f;
+                }
+            }
+        }
     }
     __syncthreads();
 }
@@ -286,7 +311,7 @@ __device__ void phase0(const Phase0Mem c, const HmyDev& st, long long c0, long l
         __syncthreads();
         if (kk < c.KS) {
             float* Tg = c.T + (size_t)g * U * TS + kk;
-            constexpr int BATCH = 8;
+            constexpr int BATCH = 16;
             for (long long base = s0 + (long long)g * BATCH; base < s1; base += (long long)NG * BATCH) {
                 float r[BATCH]; int b[BATCH];
 #pragma unroll

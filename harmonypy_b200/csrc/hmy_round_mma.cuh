@@ -36,13 +36,13 @@ struct MmaSmem {
 
 __host__ __device__ inline int hmy_odd8(int halves) { return ((halves / 8) & 1) ? halves : halves + 8; }
 
-__host__ __device__ inline MmaSmem mma_smem_plan(int d, int K, int KS, int B, int V, int nblk, int WN) {
+__host__ __device__ inline MmaSmem mma_smem_plan(int d, int K, int KS, int B, int V, int nblk, int WN, int NT) {
     MmaSmem s;
     const int dp16 = (d + 15) & ~15;
-    const int KT = (K + 7) / 8;
-    s.NTW = (WN == 1) ? KT : (KT + 1) / 2;
-    const int ntw_even = (s.NTW + 1) & ~1;
-    s.KT2 = 8 * ntw_even * WN;
+    // every warp owns exactly NT n-tiles (8 clusters each); clusters beyond K are zero padding
+    s.NTW = NT;
+    s.KT2 = 8 * NT * WN;
+    (void)K;
     s.ZSH = hmy_odd8(dp16);
     s.RSH = hmy_odd8(s.KT2);
     const int NTHR = 128 * WN;
@@ -55,7 +55,7 @@ __host__ __device__ inline MmaSmem mma_smem_plan(int d, int K, int KS, int B, in
     s.off_Os = o; o += B * s.KT2 * 4;          // running O of the round (every CTA keeps its own copy)
     s.off_rs = o; o += s.KT2 * 4;              // sum_n R[n][k] = sum of O over covariate 0
     s.off_prb = o; o += 2 * B * 4;             // Pr_b | theta
-    s.off_part = o; o += 4 * s.KT2 * 4;        // per row-group column sums at a block end
+    s.off_part = o; o += 8 * s.KT2 * 4;        // finished runs' column sums: 2 slots per row group
     s.off_rc = o; o += 16 * 4;
     o = (o + 15) & ~15;
     s.off_union = o;
@@ -100,11 +100,11 @@ __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.
 
 // x (already scaled) -> packed fp16 pairs of the hi and lo parts
 __device__ __forceinline__ void split2(float x0, float x1, unsigned int& hi, unsigned int& lo) {
-    const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-    const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-    __half2 H = __halves2half2(h0, h1), L = __halves2half2(l0, l1);
-    hi = *reinterpret_cast<unsigned int*>(&H);
-    lo = *reinterpret_cast<unsigned int*>(&L);
+    const __half2 H = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(H);
+    const __half2 L = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    hi = *reinterpret_cast<const unsigned int*>(&H);
+    lo = *reinterpret_cast<const unsigned int*>(&L);
 }
 
 // ---- per-CTA context --------------------------------------------------------------------------
@@ -119,6 +119,7 @@ struct MmaCtx {
     int n0;                             // first n-tile of this warp
     int ntw;                            // n-tiles this warp really has
     int run_combo;
+    int slot_used;                      // this row group already parked one finished run in its first slot
     float colacc[NT][2];                // running batch sums of the warp's rows (this thread's columns)
     float yacc[NT][4];                  // centroid sums Y^T[PC m-tile][cluster n-tiles], whole round
     double objd, obje;
@@ -126,7 +127,7 @@ struct MmaCtx {
 
 template <int NT, int WN>
 __device__ __forceinline__ void mma_ctx_init(MmaCtx<NT, WN>& c, const HmyDev& st, unsigned char* smem) {
-    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN);
+    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN, NT);
     c.Yh = (__half*)(smem + p.off_Yh); c.Yl = (__half*)(smem + p.off_Yl);
     c.Zh = (__half*)(smem + p.off_Zh); c.Zl = (__half*)(smem + p.off_Zl);
     c.Rh = (__half*)(smem + p.off_Rh); c.Rl = (__half*)(smem + p.off_Rl);
@@ -140,10 +141,9 @@ __device__ __forceinline__ void mma_ctx_init(MmaCtx<NT, WN>& c, const HmyDev& st
     c.ZSH = p.ZSH; c.RSH = p.RSH; c.NTW = p.NTW; c.KT2 = p.KT2;
     c.dt = (st.d + 15) >> 4;
     const int warp = threadIdx.x >> 5, nh = warp >> 2;
-    const int KT = (st.K + 7) >> 3;
-    c.n0 = nh * p.NTW;
-    c.ntw = min(p.NTW, KT - c.n0);
-    c.run_combo = -1;
+    c.n0 = nh * NT;
+    c.ntw = NT;
+    c.run_combo = -1; c.slot_used = 0;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         c.colacc[i][0] = c.colacc[i][1] = 0.f;
@@ -198,7 +198,7 @@ __device__ __forceinline__ void mma_flush_run(MmaCtx<NT, WN>& c, const HmyDev& s
         float* base = st.Dnew + (size_t)blk * st.B * st.K;
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            if (i < c.ntw) {
+            {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     float v = c.colacc[i][e];
@@ -226,38 +226,58 @@ __device__ __forceinline__ void mma_flush_run(MmaCtx<NT, WN>& c, const HmyDev& s
     c.run_combo = -1;
 }
 
-// End of a block: the running column sums of all warps leave through shared memory so that
-// every thread issues ONE atomic per covariate (a warp's atomics complete one after the other,
-// ~0.35 us each: 26 per warp per block were 10 us on the block's critical path).
+// The running column sums of a row group go to shared-memory slot `slot` (2 per row group)
 template <int NT, int WN>
-__device__ void mma_flush_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk) {
-    constexpr int NTHR = 128 * WN;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mw = warp & 3, g = lane >> 2, t = lane & 3;
+__device__ __forceinline__ void mma_park_run(MmaCtx<NT, WN>& c, int slot) {
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-        if (i < c.ntw) {
+        {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 float v = c.colacc[i][e];
                 v += __shfl_xor_sync(0xffffffffu, v, 4);
                 v += __shfl_xor_sync(0xffffffffu, v, 8);
                 v += __shfl_xor_sync(0xffffffffu, v, 16);
-                if (g == 0) c.sPart[mw * c.KT2 + 8 * (c.n0 + i) + 2 * t + e] = v;
+                if (g == 0) c.sPart[slot * c.KT2 + 8 * (c.n0 + i) + 2 * t + e] = v;
                 c.colacc[i][e] = 0.f;
             }
         }
     }
-    if (lane == 0 && warp < 4) c.sRc[mw] = c.run_combo;      // WN = 2: both column halves share the rows' combo
-    c.run_combo = -1;
+    if (lane == 0 && (threadIdx.x >> 5) < 4) c.sRc[slot] = c.run_combo;   // WN = 2: both column halves share the rows
+}
+
+// A run of equal-combination rows ended inside a block: park it (first time) or, if the row
+// group already used its spare slot, send it out with per-warp atomics (slow, rare).
+template <int NT, int WN>
+__device__ __forceinline__ void mma_end_run(MmaCtx<NT, WN>& c, const HmyDev& st, int blk) {
+    if (c.run_combo < 0) return;
+    const int mw = (threadIdx.x >> 5) & 3;
+    if (!c.slot_used) { mma_park_run(c, 2 * mw); c.slot_used = 1; c.run_combo = -1; }
+    else mma_flush_run(c, st, blk);
+}
+
+// End of a block: every parked run leaves through shared memory so that each thread issues ONE
+// atomic per covariate and run (a warp's atomics complete one after the other, ~0.35 us each:
+// 26 per warp per block were 10 us on the block's critical path).
+template <int NT, int WN>
+__device__ void mma_flush_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk) {
+    constexpr int NTHR = 128 * WN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, mw = warp & 3;
+    if (!c.slot_used && lane == 0 && warp < 4) c.sRc[2 * mw] = -1;
+    mma_park_run(c, 2 * mw + 1);
+    c.run_combo = -1; c.slot_used = 0;
     __syncthreads();
     for (int col = tid; col < st.K; col += NTHR) {
         float a = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < 8; ++w) {
             const int cb = c.sRc[w];
             if (cb < 0) continue;
             a += c.sPart[w * c.KT2 + col];
-            const int nxt = (w < 3) ? c.sRc[w + 1] : -2;
+            int nxt = -2;
+#pragma unroll
+            for (int w2 = 7; w2 > w; --w2) if (c.sRc[w2] >= 0) nxt = c.sRc[w2];   // next occupied slot
             if (nxt != cb) {
                 if (a != 0.f) {
                     for (int vv = 0; vv < st.V; ++vv) {
@@ -332,23 +352,16 @@ __device__ void mma_load_O(MmaCtx<NT, WN>& c, const HmyDev& st) {
     }
 }
 
-// One block of update_R (harmony.py:495-509) for this CTA's cells, or the init assignment
-// (harmony.py:380-389) when init = true.
+// Stage one tile: ids / combination / levels of its cells and their Z_cos rows as fp16 hi/lo.
+// Independent of the penalty table, so the first tile of the NEXT block is staged before the
+// grid barrier is waited on (its HBM latency overlaps the barrier and the table update).
 template <int NT, int WN>
-__device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, const int* list,
-                                  long long lbeg, long long lend, bool init) {
+__device__ void mma_stage_tile(MmaCtx<NT, WN>& c, const HmyDev& st, const int* list, long long tb, int nt) {
     constexpr int NTHR = 128 * WN;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int mw = warp & 3, nh = warp >> 2;
-    const int g = lane >> 2, t = lane & 3;
-    const int dp = st.dp, dp4 = dp >> 2, Kp = st.Kp, K = st.K, V = st.V;
-    const int ZSH = c.ZSH, RSH = c.RSH;
-    const int lj = lane >> 3, lr = lane & 7;            // ldmatrix: matrix index / row inside it
-    int tslot = 64;
-#define HMY_TILE_STAMP() do { if (blk == 5 && !init) hmy_trace(st, tslot < 124 ? tslot++ : 124); } while (0)
-    for (long long tb = lbeg; tb < lend; tb += HMY_MT) {
-        const int nt = (int)min((long long)HMY_MT, lend - tb);
-        HMY_TILE_STAMP();
+    const int tid = threadIdx.x;
+    const int dp = st.dp, dp4 = dp >> 2, V = st.V;
+    const int ZSH = c.ZSH;
+    {
         // ---- stage: cell ids / levels, Z_cos rows -> fp16 hi/lo tile
         if (tid < HMY_MT) {
             int cell = 0, combo = -1;
@@ -360,7 +373,6 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
             c.sCell[tid] = cell; c.sCombo[tid] = combo;
         }
         __syncthreads();
-        HMY_TILE_STAMP();
         {
             // gather: a batch of loads per thread is issued before its first conversion / store
             constexpr int ZU = 4;
@@ -389,7 +401,31 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
                 }
             }
         }
-        __syncthreads();
+    }
+    __syncthreads();
+}
+
+// One block of update_R (harmony.py:495-509) for this CTA's cells, or the init assignment
+// (harmony.py:380-389) when init = true.  staged_tb: first cell index of a tile that
+// mma_stage_tile already prepared (-1: none).
+template <int NT, int WN>
+__device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, const int* list,
+                                  long long lbeg, long long lend, bool init, long long staged_tb) {
+    constexpr int NTHR = 128 * WN;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int mw = warp & 3, nh = warp >> 2;
+    const int g = lane >> 2, t = lane & 3;
+    const int Kp = st.Kp, K = st.K, V = st.V;
+    const int ZSH = c.ZSH, RSH = c.RSH;
+    const int lj = lane >> 3, lr = lane & 7;            // ldmatrix: matrix index / row inside it
+    (void)NTHR; (void)tid;
+    int tslot = 64;
+#define HMY_TILE_STAMP() do { if (blk == 5 && !init) hmy_trace(st, tslot < 124 ? tslot++ : 124); } while (0)
+    for (long long tb = lbeg; tb < lend; tb += HMY_MT) {
+        const int nt = (int)min((long long)HMY_MT, lend - tb);
+        HMY_TILE_STAMP();
+        if (tb != staged_tb) mma_stage_tile(c, st, list, tb, nt);
+        HMY_TILE_STAMP();
         HMY_TILE_STAMP();
         const int row0 = 16 * mw;
         const bool have_rows = row0 < nt;                // warp-uniform
@@ -408,18 +444,18 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
                 ldsm_x4(al, smem_u32(c.Zl + arow * ZSH + acol));
 #pragma unroll
                 for (int ip = 0; ip < NT; ip += 2) {
-                    if (ip < c.ntw) {
+                    {
                         unsigned int bh[4], bl[4];
                         const int brow = 8 * (c.n0 + ip) + lr + 8 * (lj >> 1), bcol = 16 * ks + 8 * (lj & 1);
                         ldsm_x4(bh, smem_u32(c.Yh + brow * ZSH + bcol));
                         ldsm_x4(bl, smem_u32(c.Yl + brow * ZSH + bcol));
-                        const bool two = (ip + 1 < NT) && (ip + 1 < c.ntw);
+                        constexpr bool two = true;
                         mma_f16(acc[ip], al, bh[0], bh[1]);
-                        if (two) mma_f16(acc[ip + 1 < NT ? ip + 1 : ip], al, bh[2], bh[3]);
+                        if (two) mma_f16(acc[ip + 1], al, bh[2], bh[3]);
                         mma_f16(acc[ip], ah, bl[0], bl[1]);
-                        if (two) mma_f16(acc[ip + 1 < NT ? ip + 1 : ip], ah, bl[2], bl[3]);
+                        if (two) mma_f16(acc[ip + 1], ah, bl[2], bl[3]);
                         mma_f16(acc[ip], ah, bh[0], bh[1]);
-                        if (two) mma_f16(acc[ip + 1 < NT ? ip + 1 : ip], ah, bh[2], bh[3]);
+                        if (two) mma_f16(acc[ip + 1], ah, bh[2], bh[3]);
                     }
                 }
             }
@@ -432,7 +468,7 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
             const float* pr1 = c.Ps + lv1[0] * c.KT2;
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
-                if (i < c.ntw) {
+                {
                     const int col = 8 * (c.n0 + i) + 2 * t;
                     const float2 k1 = *reinterpret_cast<const float2*>(c.c1 + col);
                     const float2 k3 = *reinterpret_cast<const float2*>(c.c3 + col);
@@ -490,7 +526,7 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
             float oe = 0.f;
 #pragma unroll
             for (int i = 0; i < NT; ++i) {
-                if (i < c.ntw) {
+                {
                     const int col = 8 * (c.n0 + i) + 2 * t;
                     const float2 k3 = *reinterpret_cast<const float2*>(c.c3 + col);
                     const float ra0 = acc[i][0] * sc0, rb0 = acc[i][1] * sc0;
@@ -521,11 +557,11 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
                 const int cb = c.sCombo[r];
                 int e = r + 1;
                 while (e < rhi && c.sCombo[e] == cb) ++e;
-                if (cb != c.run_combo) { mma_flush_run(c, st, blk); c.run_combo = cb; }
+                if (cb != c.run_combo) { mma_end_run(c, st, blk); c.run_combo = cb; }
                 const bool in0 = (row0 + g) >= r && (row0 + g) < e, in1 = (row0 + g + 8) >= r && (row0 + g + 8) < e;
 #pragma unroll
                 for (int i = 0; i < NT; ++i) {
-                    if (i < c.ntw) {
+                    {
                         c.colacc[i][0] += (in0 ? acc[i][0] : 0.f) + (in1 ? acc[i][2] : 0.f);
                         c.colacc[i][1] += (in0 ? acc[i][1] : 0.f) + (in1 ? acc[i][3] : 0.f);
                     }
@@ -536,7 +572,7 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
             // rows of this warp are beyond the tile: their R must read as zero in the second contraction
             for (int i = lane; i < 16 * (RSH / 2); i += 32) {
                 const int rr = i / (RSH / 2), cc = 2 * (i - rr * (RSH / 2));
-                if (cc >= 8 * c.n0 && cc < 8 * (c.n0 + c.NTW + (c.NTW & 1))) {
+                if (cc >= 8 * c.n0 && cc < 8 * (c.n0 + NT)) {
                     *reinterpret_cast<unsigned int*>(c.Rh + (row0 + rr) * RSH + cc) = 0u;
                     *reinterpret_cast<unsigned int*>(c.Rl + (row0 + rr) * RSH + cc) = 0u;
                 }
@@ -556,19 +592,19 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
                 ldsm_x4_t(al, smem_u32(c.Zl + arow * ZSH + acol));
 #pragma unroll
                 for (int ip = 0; ip < NT; ip += 2) {
-                    if (ip < c.ntw) {
+                    {
                         unsigned int bh[4], bl[4];
                         // B[k = cell][n = cluster] read transposed from the [cell][cluster] tile
                         const int brow = 16 * ks + lr + 8 * (lj & 1), bcol = 8 * (c.n0 + ip) + 8 * (lj >> 1);
                         ldsm_x4_t(bh, smem_u32(c.Rh + brow * RSH + bcol));
                         ldsm_x4_t(bl, smem_u32(c.Rl + brow * RSH + bcol));
-                        const bool two = (ip + 1 < NT) && (ip + 1 < c.ntw);
+                        constexpr bool two = true;
                         mma_f16(c.yacc[ip], al, bh[0], bh[1]);
-                        if (two) mma_f16(c.yacc[ip + 1 < NT ? ip + 1 : ip], al, bh[2], bh[3]);
+                        if (two) mma_f16(c.yacc[ip + 1], al, bh[2], bh[3]);
                         mma_f16(c.yacc[ip], ah, bl[0], bl[1]);
-                        if (two) mma_f16(c.yacc[ip + 1 < NT ? ip + 1 : ip], ah, bl[2], bl[3]);
+                        if (two) mma_f16(c.yacc[ip + 1], ah, bl[2], bl[3]);
                         mma_f16(c.yacc[ip], ah, bh[0], bh[1]);
-                        if (two) mma_f16(c.yacc[ip + 1 < NT ? ip + 1 : ip], ah, bh[2], bh[3]);
+                        if (two) mma_f16(c.yacc[ip + 1], ah, bh[2], bh[3]);
                     }
                 }
             }
@@ -589,7 +625,7 @@ __device__ void mma_flush_round_sums(MmaCtx<NT, WN>& c, const HmyDev& st) {
     if (mw < c.dt) {
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-            if (i < c.ntw) {
+            {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int j = 16 * mw + g + 8 * (e >> 1), k = 8 * (c.n0 + i) + 2 * t + (e & 1);
@@ -629,7 +665,7 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
     constexpr int NTHR = 128 * WN;
     MmaCtx<NT, WN> c;
     mma_ctx_init(c, st, smem);
-    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN);
+    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN, NT);
     const unsigned int G = gridDim.x;
     const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G;
     hmy_trace(st, 0);
@@ -638,7 +674,7 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
     if (mode == 1) {
         mma_zero_tiles(c);
         __syncthreads();
-        mma_process_block(c, st, 0, nullptr, c0, c1, true);
+        mma_process_block(c, st, 0, nullptr, c0, c1, true, -1);
         mma_flush_round_sums(c, st);
         grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() { serial_finalize(st, 1, c.sRow, c.sRed); });
         return;
@@ -648,16 +684,29 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
     hmy_trace(st, 1);
     unsigned int gen = gen_base + 1u;
     mma_load_O(c, st);                       // O is only written by the finalize of the previous launch
+    mma_zero_tiles(c);
+    __syncthreads();
+    long long staged = -1;
+    {
+        long long nb, ne;
+        block_share(st, 0, blockIdx.x, G, nb, ne);
+        if (nb < ne) { mma_stage_tile(c, st, st.list, nb, (int)min((long long)HMY_MT, ne - nb)); staged = nb; }
+    }
     grid_barrier(st, G, gen++);              // all Told sums are in
     hmy_trace(st, 2);
-    mma_zero_tiles(c);
     for (int blk = 0; blk < st.nblk; ++blk) {
         mma_update_tables(c, st, blk);
         hmy_trace(st, 3 + 3 * blk);
         long long lb, le;
         block_share(st, blk, blockIdx.x, G, lb, le);
-        mma_process_block(c, st, blk, st.list, lb, le, false);
+        mma_process_block(c, st, blk, st.list, lb, le, false, staged);
         hmy_trace(st, 4 + 3 * blk);
+        staged = -1;
+        if (blk + 1 < st.nblk) {        // next block's first tile: stage before waiting at the barrier
+            long long nb, ne;
+            block_share(st, blk + 1, blockIdx.x, G, nb, ne);
+            if (nb < ne) { mma_stage_tile(c, st, st.list, nb, (int)min((long long)HMY_MT, ne - nb)); staged = nb; }
+        }
         if (blk + 1 < st.nblk) {
             grid_barrier(st, G, gen++);
         } else {
@@ -674,7 +723,7 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
     constexpr int NTHR = 128 * WN;
     MmaCtx<NT, WN> c;
     mma_ctx_init(c, st, smem);
-    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN);
+    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN, NT);
     const unsigned int G = gridDim.x;
     const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G;
     if (what == 0) {
@@ -689,9 +738,9 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
     if (what == 1) {
         long long lb, le;
         block_share(st, blk, blockIdx.x, G, lb, le);
-        mma_process_block(c, st, blk, st.list, lb, le, false);
+        mma_process_block(c, st, blk, st.list, lb, le, false, -1);
     } else {
-        mma_process_block(c, st, 0, nullptr, c0, c1, true);
+        mma_process_block(c, st, 0, nullptr, c0, c1, true, -1);
     }
     mma_flush_round_sums(c, st);
 }
