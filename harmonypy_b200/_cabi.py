@@ -26,7 +26,7 @@ SYMBOLS = {
     "hmy_destroy": (None, [C.c_void_p]),
     "hmy_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmy_set_params": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float,
-                                 C.c_float]),
+                                 C.c_double]),
     "hmy_set_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmy_init_from_centroids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_kmeans_round": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),

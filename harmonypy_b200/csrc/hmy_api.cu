@@ -40,7 +40,7 @@ struct hmy_ctx {
     bool have_data = false, have_params = false, have_init = false;
     unsigned long long seed = 0x243F6A8885A308D3ull;
     unsigned int round_counter = 0, gen = 0;
-    float block_size = 0.05f;
+    double block_size = 0.05;
     // kernels bound to the (KPT, JPW) instantiation
     const void* fn_round = nullptr; const void* fn_stage = nullptr;
     const void* fn_mom = nullptr; const void* fn_apply = nullptr;
@@ -289,11 +289,11 @@ static int plan_round(hmy_ctx* ctx) {
 }
 
 extern "C" int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* theta, const float* sigma,
-                              const float* lamb, int lambda_estimation, float alpha, float block_size) {
+                              const float* lamb, int lambda_estimation, float alpha, double block_size) {
     HmyDev& st = ctx->st;
     CK(cudaSetDevice(ctx->device));
     if (ctx->have_params) FAIL("hmy_set_params may be called once per context");
-    if (!(block_size > 0.f) || block_size > 1.f) FAIL("block_size must be in (0, 1]");
+    if (!(block_size > 0.0) || block_size > 1.0) FAIL("block_size must be in (0, 1]");
     ctx->block_size = block_size;
     CK(cudaMemcpy(st.Pr_b, Pr_b, st.B * sizeof(float), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(st.theta, theta, st.B * sizeof(float), cudaMemcpyHostToDevice));

@@ -69,7 +69,7 @@ __host__ __device__ inline MmaSmem mma_smem_plan(int d, int K, int KS, int B, in
     s.off_lev = a; a += HMY_MT * V * 4;
     s.off_xch = a; a += 2 * 2 * HMY_MT * 4;
     int b = o;
-    s.off_T = b; b += phase0_tables(KS) * nblk * KS * 4;
+    s.off_T = b; if (nblk > 32) b += phase0_tables(KS) * nblk * KS * 4;
     s.off_cnt = b; s.off_btot = b;
     (void)NTHR;
     o = (a > b ? a : b);
@@ -349,6 +349,121 @@ __device__ void mma_load_O(MmaCtx<NT, WN>& c, const HmyDev& st) {
             const int i = i0 + u * NTHR;
             if (i < n) { const int b = i / K, k = i - b * K; c.Os[b * c.KT2 + k] = (float)o[u]; }
         }
+    }
+}
+
+// ---- phase 0 on the tensor cores -------------------------------------------------------------
+// Told[blk][level][k] = sum over this CTA's cells of [cell in blk] * R_old[cell][k]
+// (the R_block.sum / R_block @ Phi_block.T of harmony.py:491-492 for all blocks at once) is the
+// product onehot(blk)^T (nblk x cells) . R_old (cells x K): A is built in registers from the
+// block ids (exact in fp16), B is the fp16 hi/lo split of the R rows, which stream in
+// contiguously (cells are stored sorted, a combination segment is one HBM range).
+// Needs nblk <= 32 (two m-tiles); larger block counts use the scalar phase0<> above.
+template <int NT, int WN>
+__device__ void mma_phase0(MmaCtx<NT, WN>& c, const HmyDev& st, long long c0, long long c1) {
+    constexpr int NTHR = 128 * WN, W = 4 * WN, NP = NT * WN / 2, PP = (NP + W - 1) / W;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int lj = lane >> 3, lr = lane & 7;
+    const int Kp = st.Kp, Kp4 = Kp >> 2, RSH = c.RSH;
+    unsigned char* sB = reinterpret_cast<unsigned char*>(c.sCell);       // 64 block ids of the tile
+    long long s0 = c0;
+    while (s0 < c1) {
+        const int combo = st.combo[s0];
+        const long long s1 = min(c1, st.combo_start[combo + 1]);
+        float acc[2][2 * PP][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 2 * PP; ++j) acc[m][j][0] = acc[m][j][1] = acc[m][j][2] = acc[m][j][3] = 0.f;
+        // R rows of a tile: all loads of a thread in one batch, issued one tile ahead of their use
+        constexpr int RU = 16;                                         // 64 rows x (Kp4 <= 32 WN) float4 / NTHR
+        float4 v[RU];
+        unsigned char bnext = 255;
+        auto issue = [&](long long tb) {
+            const int nt = (int)min((long long)HMY_MT, s1 - tb);
+            const float4* src = reinterpret_cast<const float4*>(st.R + (size_t)tb * Kp);
+            const int total = nt * Kp4;
+#pragma unroll
+            for (int u = 0; u < RU; ++u) { const int i = tid + u * NTHR; if (i < total) v[u] = __ldg(src + i); }
+            if (tid < HMY_MT) bnext = (tid < nt) ? st.blk[tb + tid] : (unsigned char)255;
+        };
+        issue(s0);
+        for (long long tb = s0; tb < s1; tb += HMY_MT) {
+            const int nt = (int)min((long long)HMY_MT, s1 - tb);
+            {
+                const int total = nt * Kp4;
+#pragma unroll
+                for (int u = 0; u < RU; ++u) {
+                    const int i = tid + u * NTHR;
+                    if (i < total) {
+                        const int row = i / Kp4, c4 = i - row * Kp4;
+                        uint2 hi, lo;
+                        split2(v[u].x * HMY_OPSCALE, v[u].y * HMY_OPSCALE, hi.x, lo.x);
+                        split2(v[u].z * HMY_OPSCALE, v[u].w * HMY_OPSCALE, hi.y, lo.y);
+                        *reinterpret_cast<uint2*>(c.Rh + row * RSH + 4 * c4) = hi;
+                        *reinterpret_cast<uint2*>(c.Rl + row * RSH + 4 * c4) = lo;
+                    }
+                }
+                if (tid < HMY_MT) sB[tid] = bnext;
+            }
+            if (tb + HMY_MT < s1) issue(tb + HMY_MT);
+            __syncthreads();
+            const int ksteps = (nt + 15) >> 4;
+            for (int ks = 0; ks < ksteps; ++ks) {
+                // A[m = block][k = cell]: 1 where the cell belongs to the block
+                const unsigned int b01 = *reinterpret_cast<const unsigned short*>(sB + 16 * ks + 2 * t);
+                const unsigned int b23 = *reinterpret_cast<const unsigned short*>(sB + 16 * ks + 2 * t + 8);
+                const unsigned int k0 = b01 & 255u, k1 = b01 >> 8, k2 = b23 & 255u, k3 = b23 >> 8;
+                unsigned int a[2][4];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const unsigned int rl = 16 * m + g, rh = rl + 8;
+                    a[m][0] = (k0 == rl ? 0x3C00u : 0u) | (k1 == rl ? 0x3C000000u : 0u);
+                    a[m][1] = (k0 == rh ? 0x3C00u : 0u) | (k1 == rh ? 0x3C000000u : 0u);
+                    a[m][2] = (k2 == rl ? 0x3C00u : 0u) | (k3 == rl ? 0x3C000000u : 0u);
+                    a[m][3] = (k2 == rh ? 0x3C00u : 0u) | (k3 == rh ? 0x3C000000u : 0u);
+                }
+#pragma unroll
+                for (int jp = 0; jp < PP; ++jp) {
+                    const int p = warp + W * jp;
+                    if (p < NP) {
+                        unsigned int bh[4], bl[4];
+                        const int brow = 16 * ks + lr + 8 * (lj & 1), bcol = 16 * p + 8 * (lj >> 1);
+                        ldsm_x4_t(bh, smem_u32(c.Rh + brow * RSH + bcol));
+                        ldsm_x4_t(bl, smem_u32(c.Rl + brow * RSH + bcol));
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            mma_f16(acc[m][2 * jp], a[m], bh[0], bh[1]);
+                            mma_f16(acc[m][2 * jp + 1], a[m], bh[2], bh[3]);
+                            mma_f16(acc[m][2 * jp], a[m], bl[0], bl[1]);
+                            mma_f16(acc[m][2 * jp + 1], a[m], bl[2], bl[3]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // this segment's sums -> Told (rows = blocks, fragment layout)
+        int lev[HMY_MAX_V];
+#pragma unroll
+        for (int vv = 0; vv < HMY_MAX_V; ++vv) lev[vv] = (vv < st.V) ? st.combo_lev[combo * st.V + vv] : 0;
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int j = 0; j < 2 * PP; ++j) {
+                const int p = warp + W * (j >> 1);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int row = 16 * m + g + 8 * (e >> 1), col = 16 * p + 8 * (j & 1) + 2 * t + (e & 1);
+                    const float v = acc[m][j][e] * (1.0f / HMY_OPSCALE);
+                    if (p < NP && row < st.nblk && col < st.K && v != 0.f) {
+#pragma unroll
+                        for (int vv = 0; vv < HMY_MAX_V; ++vv)
+                            if (vv < st.V) atomicAdd(&st.Told[((size_t)row * st.B + lev[vv]) * st.K + col], v);
+                    }
+                }
+            }
+        s0 = s1;
     }
 }
 
@@ -679,13 +794,19 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
         grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() { serial_finalize(st, 1, c.sRow, c.sRed); });
         return;
     }
-    phase0<NTHR>(Phase0Mem{(float*)(smem + p.off_T), (unsigned int*)(smem + p.off_cnt), (int*)(smem + p.off_btot), st.KS},
-                 st, c0, c1);
+    mma_zero_tiles(c);
+    __syncthreads();
+    if (st.nblk <= 32) {
+        mma_phase0(c, st, c0, c1);
+    } else {
+        phase0<NTHR>(Phase0Mem{(float*)(smem + p.off_T), (unsigned int*)(smem + p.off_cnt), (int*)(smem + p.off_btot), st.KS},
+                     st, c0, c1);
+        mma_zero_tiles(c);
+        __syncthreads();
+    }
     hmy_trace(st, 1);
     unsigned int gen = gen_base + 1u;
     mma_load_O(c, st);                       // O is only written by the finalize of the previous launch
-    mma_zero_tiles(c);
-    __syncthreads();
     long long staged = -1;
     {
         long long nb, ne;
@@ -727,8 +848,14 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
     const unsigned int G = gridDim.x;
     const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G;
     if (what == 0) {
-        phase0<NTHR>(Phase0Mem{(float*)(smem + p.off_T), (unsigned int*)(smem + p.off_cnt), (int*)(smem + p.off_btot), st.KS},
-                     st, c0, c1);
+        if (st.nblk <= 32) {
+            mma_zero_tiles(c);
+            __syncthreads();
+            mma_phase0(c, st, c0, c1);
+        } else {
+            phase0<NTHR>(Phase0Mem{(float*)(smem + p.off_T), (unsigned int*)(smem + p.off_cnt), (int*)(smem + p.off_btot), st.KS},
+                         st, c0, c1);
+        }
         return;
     }
     mma_load_centroids(c, st);

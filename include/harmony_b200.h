@@ -63,7 +63,7 @@ int hmy_set_stream(hmy_ctx* ctx, void* cuda_stream);
 /* Run parameters (harmony.py:242, :262-271): Pr_b[B], theta[B], sigma[K], lamb[B+1]
  * (lamb[0] is the intercept's 0; ignored when lambda_estimation != 0, harmony.py:541-544). */
 int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* theta, const float* sigma,
-                   const float* lamb, int lambda_estimation, float alpha, float block_size);
+                   const float* lamb, int lambda_estimation, float alpha, double block_size);
 
 /* Upload this rank's cells: Z (n_local x d, fp32) and level codes (V x n_local, int32).
  * Builds Z_cos (harmony.py:234-238).  Replaces the dense Phi / Phi_moe / batch_index

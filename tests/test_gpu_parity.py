@@ -154,6 +154,30 @@ def test_one_iteration_against_fp64_oracle(N, d, levels, K, kw):
     assert rel_max(ho.Y.T, orc.Y.T) < 2e-5
 
 
+@pytest.mark.parametrize("block_size", [0.02, 0.3, 0.5])
+def test_block_size_variants_against_fp64_oracle(block_size):
+    """block_size 0.02 -> 50 blocks (scalar phase-0 fallback), 0.3 -> 4 ragged blocks, 0.5 -> 2 blocks.
+    (block_size = 1 removes every cell before re-assigning it: O - O is rounding noise, the
+    penalty is then noise in the reference as well, so it is not a meaningful parity case.)"""
+    from harmonypy_b200.harmony import Harmony, prepare_problem
+    from harmonypy_b200.synthetic import make_synthetic
+    from oracle.harmony_oracle import torch_perm_source
+    N, d, K = 7000, 24, 40
+    Z, meta = make_synthetic(N, d, [5], seed=2)
+    prob, _ = prepare_problem(pd.DataFrame(Z), meta, ["var0"], nclust=K)
+    Y0 = Z[np.random.default_rng(4).choice(N, K, replace=False)]
+    ho = Harmony(prob, 0.2, 1, 3, 1e-5, 1e-4, block_size, False, 8, 0, run=False)
+    orc = _oracle_for(prob, block_size=block_size)
+    ho.init_cluster(8, Y0); orc.init_from_centroids(Y0.T)
+    src = torch_perm_source(N, 8)
+    for r in range(3):
+        ho.kmeans_round(); orc.kmeans_round(src())
+    assert rel_max(ho.R, orc.R.T) < 3e-4 and rel_max(ho.O, orc.O) < 5e-5
+    np.testing.assert_allclose(ho.objective_kmeans, orc.objective_kmeans, rtol=2e-5)
+    ho.moe_correct_ridge(); orc.moe_correct_ridge()
+    assert rel_max(ho.Z_corr, orc.Z_corr.T) < 2e-5
+
+
 def test_run_harmony_end_to_end_like_reference_test():
     """The reference's own acceptance test shape (tests/test_harmony.py:24-30, :94-130):
     run_harmony(data, meta, [batch]) with defaults incl. the sklearn init; the corrected PCs
