@@ -1,0 +1,64 @@
+"""Cells sharded over 2 GPUs (one process per GPU, NCCL): the staged multi-GPU mode must give
+the single-GPU / reference result.  Needs >= 2 CUDA devices (skipped otherwise)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import load_case, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _worker(rank, world, port, q, name):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from harmonypy_b200.harmony import Harmony, Problem
+        inp, gold = load_case(name)
+        prob = Problem(Z=inp["Z"], codes=inp["codes"], levels=inp["levels"], level_names=[], Pr_b=inp["Pr_b"],
+                       theta=inp["theta"], lamb=inp["lamb"], lambda_estimation=bool(inp["lambda_estimation"]),
+                       sigma=inp["sigma"], K=int(inp["K"]))
+        ho = Harmony(prob, float(inp["alpha"]), int(inp["max_iter_harmony"]), int(inp["max_iter_kmeans"]),
+                     float(inp["epsilon_kmeans"]), float(inp["epsilon_harmony"]), float(inp["block_size"]), False,
+                     int(inp["random_state"]), rank, comm=True, init_centroids=inp["Y0"])
+        Zc = ho.Z_corr                      # gathered over ranks
+        q.put(dict(rank=rank, rounds=list(ho.kmeans_rounds), Z=Zc, obj=list(ho.objective_harmony),
+                   lo=ho._lo, hi=ho._hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["synth", "pbmc"])
+def test_two_gpus_match_reference(name):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, name)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=600) for _ in procs], key=lambda o: o["rank"])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    inp, gold = load_case(name)
+    a, b = outs
+    assert a["rounds"] == b["rounds"] == list(gold["kmeans_rounds"])
+    np.testing.assert_array_equal(a["Z"], b["Z"])
+    err = rel_max(a["Z"][gold["final_cells"]], gold["Zcorr_final"])
+    print(f"\n[{name}] 2-GPU staged mode: final Z_corr vs reference fp32 {err:.3e}")
+    assert err < 1e-4
+    np.testing.assert_allclose(a["obj"], gold["objective_harmony"], rtol=5e-5)
