@@ -348,7 +348,9 @@ def run_ours(args, w):
                        "perm_mode": "device", "l2": "inputs larger than L2 (R 400 MB + Z 600 MB per GPU), no flush",
                        "init": f"sklearn k-means++ on a {min(N_total, INIT_SUBSAMPLE)}-cell subsample, untimed",
                        "iterations_per_step": tot_iters / args.steps, "rounds_per_step": tot_rounds / args.steps,
-                       "mode": ("staged launches + NCCL all-reduce of the K x B tables per block (exact multi-GPU mode)" if world > 1
+                       "mode": ("persistent round kernel with in-kernel NVLink exchange of the K x B tables (fused, exact)"
+                                if eng.counter("fused") == 1 else
+                                "staged launches + NCCL all-reduce of the K x B tables per block (exact multi-GPU mode)" if world > 1
                                 else "staged launches" if args.staged else "persistent round kernel")},
             "cell_rounds_per_s": n_local * world * n_rounds / (ms_round / 1e3) if ms_round > 0 else None,
             "ridge_passes_per_s": n_local * world * n_ridge / (ms_ridge / 1e3) if ms_ridge > 0 else None,

@@ -171,6 +171,18 @@ class Engine:
     def timer_ms(self, name):
         return float(self.lib.hmy_timer_ms(self.h, name.encode()))
 
+    def comm_export(self):
+        """64-byte IPC handle of this rank's exchange buffer (fused multi-GPU mode)."""
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.hmy_comm_export(self.h, buf), "hmy_comm_export")
+        return buf.raw
+
+    def comm_attach(self, rank, world, handles):
+        """handles: the world x 64 bytes of every rank's comm_export(), in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._ck(self.lib.hmy_comm_attach(self.h, int(rank), int(world), blob), "hmy_comm_attach")
+
     def set_allreduce(self, pyfunc):
         """pyfunc(dev_ptr:int, count:int, dtype:int, stream:int) -> 0 on success."""
         def tramp(user, ptr, count, dtype, stream):

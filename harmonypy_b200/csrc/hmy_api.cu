@@ -16,6 +16,7 @@
 #include "hmy_round.cuh"
 #include "hmy_round_mma.cuh"
 #include "hmy_ridge.cuh"
+#include "hmy_ridge_mma.cuh"
 
 #define HMY_VERSION "harmony_b200 0.1.0 (sm_100a)"
 
@@ -31,18 +32,19 @@ struct hmy_ctx {
     std::vector<int> levels, level_off;
     int KPT = 0, JPW = 0;
     int WN = 1, NT = 0, round_threads = HMY_THREADS;
-    bool use_mma = false, want_mma = true;
+    bool use_mma = false, want_mma = true, ridge_mma = false, want_ridge_mma = true;
+    float zscale = 1.f;
     int force_wn = 0;
     int G = 0, sms = 0;
     int smem_round = 0, smem_mom = 0, smem_apply = 0, smem_solve = 0;
-    int grid_ridge = 0;
+    int grid_ridge = 0, grid_mom = 0, ridge_threads = HMY_THREADS;
     bool persistent = true;
     bool have_data = false, have_params = false, have_init = false;
     unsigned long long seed = 0x243F6A8885A308D3ull;
     unsigned int round_counter = 0, gen = 0;
     double block_size = 0.05;
     // kernels bound to the (KPT, JPW) instantiation
-    const void* fn_round = nullptr; const void* fn_stage = nullptr;
+    const void* fn_round = nullptr; const void* fn_stage = nullptr; const void* fn_round_fused = nullptr;
     const void* fn_mom = nullptr; const void* fn_apply = nullptr;
     // device buffers
     std::vector<void*> allocs;
@@ -62,6 +64,10 @@ struct hmy_ctx {
     double ms_round = 0.0, ms_ridge = 0.0, ms_init = 0.0;
     // multi-GPU
     hmy_allreduce_fn ar = nullptr; void* ar_user = nullptr;
+    unsigned char* xbuf = nullptr; size_t xbytes = 0;      // this rank's exchange buffer
+    std::vector<void*> xopened;                            // peers' buffers opened through IPC
+    bool fused = false;
+    unsigned int xseq = 0;
 };
 
 #define CK(call)                                                                                   \
@@ -107,7 +113,7 @@ static bool bind_mma(hmy_ctx* ctx) {
     ctx->WN = (st.K <= 128) ? 1 : 2;
     if (ctx->force_wn == 2 && KT >= 2) ctx->WN = 2;
     const int ntw = (ctx->WN == 1) ? KT : (KT + 1) / 2;
-    const void* f[2] = {nullptr, nullptr};
+    const void* f[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (ctx->WN == 1) {
         if (ntw <= 4) { hmy_bind_mma_4_1(f); ctx->NT = 4; } else if (ntw <= 8) { hmy_bind_mma_8_1(f); ctx->NT = 8; }
         else if (ntw <= 14) { hmy_bind_mma_14_1(f); ctx->NT = 14; } else { hmy_bind_mma_16_1(f); ctx->NT = 16; }
@@ -115,9 +121,14 @@ static bool bind_mma(hmy_ctx* ctx) {
         if (ntw <= 8) { hmy_bind_mma_8_2(f); ctx->NT = 8; } else if (ntw <= 14) { hmy_bind_mma_14_2(f); ctx->NT = 14; }
         else { hmy_bind_mma_16_2(f); ctx->NT = 16; }
     }
-    ctx->fn_round = f[0]; ctx->fn_stage = f[1];
+    ctx->fn_round = f[0]; ctx->fn_stage = f[1]; ctx->fn_round_fused = f[4];
     ctx->round_threads = 128 * ctx->WN;
     ctx->use_mma = true;
+    ctx->ridge_mma = false;
+    if (st.d <= 63 && ctx->want_ridge_mma) {
+        ctx->fn_mom = f[2]; ctx->fn_apply = f[3];
+        ctx->ridge_mma = true;
+    }
     return true;
 }
 
@@ -186,6 +197,7 @@ static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_glob
     if (dev_alloc(ctx, &st.sigma, (size_t)K)) return 1;
     if (dev_alloc(ctx, &st.lamb, (size_t)B + 1)) return 1;
     if (dev_alloc(ctx, &st.W, (size_t)B * K * st.dp)) return 1;
+    if (dev_alloc(ctx, &st.wmax, 4)) return 1;
     if (dev_alloc(ctx, &st.bar_count, 2)) return 1;
     st.bar_gen = st.bar_count + 1;
     CK(cudaMemset(st.bar_count, 0, 2 * sizeof(unsigned int)));
@@ -208,8 +220,6 @@ static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_glob
     ctx->smem_apply = ridge_smem_plan(K, st.KS, ctx->JPW, true).total;
     ctx->smem_solve = (int)(((size_t)(B + 1) * (B + 1 + d) + (B + 1)) * sizeof(double));
     if (ctx->smem_solve > 200 * 1024) FAIL("ridge system too large for shared memory ((B+1)*(B+1+d) doubles > 200 KB)");
-    CK(cudaFuncSetAttribute(ctx->fn_mom, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_mom));
-    CK(cudaFuncSetAttribute(ctx->fn_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_apply));
     CK(cudaFuncSetAttribute((const void*)k_ridge_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_solve));
     return 0;
 }
@@ -232,6 +242,8 @@ extern "C" void hmy_destroy(hmy_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    for (void* p : ctx->xopened) cudaIpcCloseMemHandle(p);
+    if (ctx->xbuf) cudaFree(ctx->xbuf);
     for (void* p : ctx->allocs) cudaFree(p);
     if (ctx->d_perm) cudaFree(ctx->d_perm);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
@@ -261,6 +273,7 @@ static int plan_round(hmy_ctx* ctx) {
                                    : round_smem_plan(st.dp, st.KS, st.B, st.V, nblk, ctx->JPW).total;
     if (ctx->smem_round > 227 * 1024) FAIL("round kernel needs more than 227 KB of shared memory for this (K, B, d, block_size)");
     CK(cudaFuncSetAttribute(ctx->fn_round, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
+    if (ctx->use_mma) CK(cudaFuncSetAttribute(ctx->fn_round_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
     CK(cudaFuncSetAttribute(ctx->fn_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
     int nb = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, ctx->round_threads, ctx->smem_round));
@@ -282,9 +295,22 @@ static int plan_round(hmy_ctx* ctx) {
         CK(cudaFuncSetAttribute((const void*)k_block_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     }
     if (dev_alloc(ctx, &ctx->d_cnt, (size_t)ctx->list_chunks * nblk)) return 1;
-    int nbr = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbr, ctx->fn_apply, HMY_THREADS, ctx->smem_apply));
+    if (ctx->ridge_mma) {
+        ctx->smem_mom = ridge_mma_plan(st.d, ctx->WN, ctx->NT, false).total;
+        ctx->smem_apply = ridge_mma_plan(st.d, ctx->WN, ctx->NT, true).total;
+        if (ctx->smem_apply > 227 * 1024) FAIL("ridge apply kernel needs more than 227 KB of shared memory");
+    } else {
+        ctx->smem_mom = ridge_smem_plan(st.K, st.KS, ctx->JPW, false).total;
+        ctx->smem_apply = ridge_smem_plan(st.K, st.KS, ctx->JPW, true).total;
+    }
+    ctx->ridge_threads = ctx->ridge_mma ? 128 * ctx->WN : HMY_THREADS;
+    CK(cudaFuncSetAttribute(ctx->fn_mom, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_mom));
+    CK(cudaFuncSetAttribute(ctx->fn_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_apply));
+    int nbr = 0, nbm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbr, ctx->fn_apply, ctx->ridge_threads, ctx->smem_apply));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbm, ctx->fn_mom, ctx->ridge_threads, ctx->smem_mom));
     ctx->grid_ridge = std::max(1, nbr) * ctx->sms;
+    ctx->grid_mom = std::max(1, nbm) * ctx->sms;
     return 0;
 }
 
@@ -364,6 +390,13 @@ extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* co
     CK(cudaMemcpy(st.combo, combo.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(st.order, order.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(st.pos_of, pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+    {   // scale of the fp16 split of Z_orig in the tensor-core ridge passes: hi part below 2^14
+        float zm = 0.f;
+        const size_t nz = (size_t)N * st.d;
+        for (size_t i = 0; i < nz; ++i) { const float a = std::fabs(Z_host[i]); if (a > zm && std::isfinite(a)) zm = a; }
+        int e = 0; std::frexp(std::max(zm, 1e-30f), &e);
+        ctx->zscale = std::ldexp(1.0f, 13 - e);
+    }
     // raw rows -> sorted padded layout + Z_cos
     float* raw = nullptr;
     CK(cudaMalloc((void**)&raw, (size_t)N * st.d * sizeof(float)));
@@ -461,10 +494,12 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
     CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
     CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
     if (timer_begin(ctx, ctx->ev_init)) return 1;
-    if (ctx->persistent && !ctx->ar) {
+    if (ctx->persistent && (!ctx->ar || ctx->fused)) {
+        st.xseq_base = ctx->xseq;
+        if (ctx->fused) ctx->xseq += 2;
         HmyDev s = st; int mode = 1; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
+        if (launch(ctx, ctx->fused ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
         ctx->gen += 1;
     } else {
         if (staged_round(ctx, 2, 0)) return 1;
@@ -507,10 +542,12 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
     CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
     CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
     if (timer_begin(ctx, ctx->ev_round)) return 1;
-    if (ctx->persistent && !ctx->ar) {
+    if (ctx->persistent && (!ctx->ar || ctx->fused)) {
+        st.xseq_base = ctx->xseq;
+        if (ctx->fused) ctx->xseq += (unsigned int)st.nblk + 2u;
         HmyDev s = st; int mode = 0; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
+        if (launch(ctx, ctx->fused ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
         ctx->gen += (unsigned int)st.nblk + 1u;
     } else {
         const int64_t nT = (int64_t)st.nblk * st.B * st.K, BK = (int64_t)st.B * st.K;
@@ -540,10 +577,12 @@ extern "C" int hmy_ridge_correct(hmy_ctx* ctx) {
     CK(cudaMemsetAsync(ctx->zero_ridge, 0, ctx->zero_ridge_bytes, ctx->stream));
     CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
     if (timer_begin(ctx, ctx->ev_ridge)) return 1;
-    const int grid = std::min(ctx->grid_ridge, std::max(1, st.nseg));
+    const int grid_m = std::min(ctx->grid_mom, std::max(1, st.nseg));
+    const int grid_a = std::min(ctx->grid_ridge, std::max(1, st.nseg));
+    CK(cudaMemsetAsync(st.wmax, 0, sizeof(float), ctx->stream));
     {
-        HmyDev s = st; void* args[] = {&s};
-        if (launch(ctx, ctx->fn_mom, dim3(grid), dim3(HMY_THREADS), args, ctx->smem_mom, false)) return 1;
+        HmyDev s = st; float zs = ctx->zscale; void* args[] = {&s, &zs};
+        if (launch(ctx, ctx->fn_mom, dim3(grid_m), dim3(ctx->ridge_threads), args, ctx->smem_mom, false)) return 1;
     }
     {
         const int64_t nG = (int64_t)st.K * (st.B + 1) * (st.B + 1), nM = (int64_t)(st.B + 1) * st.K * st.dp;
@@ -554,8 +593,8 @@ extern "C" int hmy_ridge_correct(hmy_ctx* ctx) {
         if (launch(ctx, (const void*)k_ridge_solve, dim3(st.K), dim3(128), args, ctx->smem_solve, false)) return 1;
     }
     {
-        HmyDev s = st; void* args[] = {&s};
-        if (launch(ctx, ctx->fn_apply, dim3(grid), dim3(HMY_THREADS), args, ctx->smem_apply, false)) return 1;
+        HmyDev s = st; const float* wm = st.wmax; void* args[] = {&s, &wm};
+        if (launch(ctx, ctx->fn_apply, dim3(grid_a), dim3(ctx->ridge_threads), args, ctx->smem_apply, false)) return 1;
     }
     if (allreduce(ctx, st.Yacc, (int64_t)st.K * st.dp, 1)) return 1;
     {
@@ -668,6 +707,10 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
         }
         return 0;
     }
+    if (n == "ridge_mma") {
+        if (ctx->have_params) FAIL("option ridge_mma must be set before hmy_set_params");
+        ctx->want_ridge_mma = value != 0; return 0;
+    }
     if (n == "mma_wn") {
         if (ctx->have_params) FAIL("option mma_wn must be set before hmy_set_params");
         ctx->force_wn = (int)value; return 0;
@@ -696,10 +739,12 @@ extern "C" int64_t hmy_counter(const hmy_ctx* ctx, const char* name) {
     if (n == "rounds") return ctx->rounds;
     if (n == "ridge_passes") return ctx->ridge_passes;
     if (n == "grid") return ctx->G;
+    if (n == "fused") return ctx->fused ? 1 : 0;
     if (n == "smem_round") return ctx->smem_round;
     if (n == "nblk") return ctx->st.nblk;
     if (n == "ncombo") return ctx->st.ncombo;
     if (n == "mma") return ctx->use_mma ? 1 : 0;
+    if (n == "ridge_mma") return ctx->ridge_mma ? 1 : 0;
     if (n == "round_threads") return ctx->round_threads;
     return -1;
 }
@@ -722,11 +767,43 @@ extern "C" int hmy_set_allreduce(hmy_ctx* ctx, hmy_allreduce_fn fn, void* user) 
 }
 
 extern "C" int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B) {
-    (void)handle_out_64B;
-    FAIL("hmy_comm_export: fused peer exchange is not built in this version");
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_params) FAIL("hmy_comm_export: call hmy_set_params first");
+    if (!ctx->use_mma) FAIL("hmy_comm_export: the fused exchange needs the tensor-core round kernel (d <= 64)");
+    if (!handle_out_64B) FAIL("hmy_comm_export: NULL handle");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!ctx->xbuf) {
+        size_t slot = (size_t)st.nblk * st.B * st.K * sizeof(float);
+        slot = std::max(slot, (size_t)(4 + (size_t)st.B * st.K) * sizeof(double));
+        slot = std::max(slot, (size_t)st.K * st.dp * sizeof(double));
+        slot = (slot + 255) & ~(size_t)255;
+        st.xslot = slot;
+        ctx->xbytes = HMY_XPAYLOAD_OFF + 2 * (size_t)HMY_MAX_WORLD * slot;
+        CK(cudaMalloc((void**)&ctx->xbuf, ctx->xbytes));
+        CK(cudaMemset(ctx->xbuf, 0, ctx->xbytes));
+    }
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->xbuf));
+    std::memcpy(handle_out_64B, &h, 64);
+    return 0;
 }
 
 extern "C" int hmy_comm_attach(hmy_ctx* ctx, int rank, int world, const void* all_handles) {
-    (void)rank; (void)world; (void)all_handles;
-    FAIL("hmy_comm_attach: fused peer exchange is not built in this version");
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->xbuf) FAIL("hmy_comm_attach: call hmy_comm_export first");
+    if (world < 1 || world > HMY_MAX_WORLD || rank < 0 || rank >= world) FAIL("hmy_comm_attach: bad rank / world (<= 8 ranks)");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { st.xpeer[r] = ctx->xbuf; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const unsigned char*)all_handles + (size_t)r * 64, 64);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->xopened.push_back(p);
+        st.xpeer[r] = (unsigned char*)p;
+    }
+    st.xrank = rank; st.xworld = world;
+    ctx->fused = world > 1;
+    return 0;
 }

@@ -22,6 +22,9 @@
 #define HMY_MAX_V 8
 #define HMY_MAX_NBLK 250
 #define HMY_TRACE_SLOTS 128
+#define HMY_MAX_WORLD 8
+#define HMY_XFLAG_STRIDE 128     // bytes between the per-source flags of an exchange buffer
+#define HMY_XPAYLOAD_OFF 4096
 
 struct HmyDev {
     long long N;             // cells on this rank
@@ -53,10 +56,16 @@ struct HmyDev {
     double* Gram;            // [K][B+1][B+1]
     double* Mom;             // [B+1][K][dp]
     float* W;                // [B][K][dp]
+    float* wmax;             // max |W| of the last solve
     // grid barrier
     unsigned int* bar_count; unsigned int* bar_gen;
     // optional per-CTA timeline (globaltimer ns), [grid][HMY_TRACE_SLOTS]; nullptr = off
     unsigned long long* trace;
+    // fused multi-GPU exchange: peer-mapped exchange buffers (own one included), see hmy_xchg.cuh
+    unsigned char* xpeer[HMY_MAX_WORLD];
+    int xrank, xworld;
+    unsigned int xseq_base;          // sequence number of the last exchange before this launch
+    unsigned long long xslot;        // bytes of one payload slot
 };
 
 __device__ __forceinline__ void hmy_trace(const HmyDev& st, int slot) {

@@ -3,6 +3,7 @@
 #include "hmy_common.cuh"
 #include "hmy_round.cuh"
 #include "hmy_round_mma.cuh"
+#include "hmy_ridge_mma.cuh"
 
 #ifndef HMY_NT
 #error "compile with -DHMY_NT=.. -DHMY_WN=.."
@@ -11,6 +12,9 @@
 #define HMY_CATM(a, b) HMY_CATM2(a, b)
 
 extern "C" void HMY_CATM(HMY_NT, HMY_WN)(const void** fns) {
-    fns[0] = (const void*)k_round_mma<HMY_NT, HMY_WN>;
+    fns[0] = (const void*)k_round_mma<HMY_NT, HMY_WN, false>;
+    fns[4] = (const void*)k_round_mma<HMY_NT, HMY_WN, true>;
     fns[1] = (const void*)k_round_mma_stage<HMY_NT, HMY_WN>;
+    fns[2] = (const void*)k_ridge_moments_mma<HMY_NT, HMY_WN>;
+    fns[3] = (const void*)k_ridge_apply_mma<HMY_NT, HMY_WN>;
 }

@@ -193,10 +193,17 @@ __global__ void __launch_bounds__(128) k_ridge_solve(HmyDev st) {
         __syncthreads();
     }
     // W[b][k][j]; the intercept row is dropped (harmony.py:565)
+    float wm = 0.f;
     for (int i = threadIdx.x; i < st.B * st.dp; i += blockDim.x) {
         const int b = i / st.dp, j = i - b * st.dp;
-        st.W[((size_t)b * st.K + k) * st.dp + j] = (j < d) ? (float)A[(size_t)(1 + b) * m + n + j] : 0.f;
+        const float w = (j < d) ? (float)A[(size_t)(1 + b) * m + n + j] : 0.f;
+        st.W[((size_t)b * st.K + k) * st.dp + j] = w;
+        if (isfinite(w)) wm = fmaxf(wm, fabsf(w));
     }
+    // largest |coefficient| (scale of the fp16 coefficient tile of the tensor-core apply pass)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+    if ((threadIdx.x & 31) == 0 && st.wmax != nullptr) atomicMax(reinterpret_cast<unsigned int*>(st.wmax), __float_as_uint(wm));
 }
 
 #endif  // HMY_NONTEMPLATE_KERNELS

@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include "hmy_common.cuh"
 #include "hmy_round.cuh"
+#include "hmy_xchg.cuh"
 
 #define HMY_MT 64                 // cells per tile
 #define HMY_OPSCALE 1024.0f       // operand scale before the fp16 split (2^10)
@@ -774,7 +775,9 @@ __device__ __forceinline__ void mma_load_penalty(MmaCtx<NT, WN>& c, const HmyDev
 }
 
 // ---- kernels ---------------------------------------------------------------------------------
-template <int NT, int WN>
+// FUSED: exchange the K x B tables with the other GPUs inside the grid barriers (hmy_xchg.cuh);
+// a separate instantiation so that the single-GPU kernel carries none of that code.
+template <int NT, int WN, bool FUSED>
 __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_round_mma(HmyDev st, int mode, unsigned int gen_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NTHR = 128 * WN;
@@ -791,7 +794,13 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
         __syncthreads();
         mma_process_block(c, st, 0, nullptr, c0, c1, true, -1);
         mma_flush_round_sums(c, st);
-        grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() { serial_finalize(st, 1, c.sRow, c.sRed); });
+        grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() {
+            if (FUSED && st.xworld > 1) {
+                xchg_allreduce<double>(st, st.obj, 4 + st.B * st.K, st.xseq_base + 1u);     // objective sums | Ofresh
+                xchg_allreduce<double>(st, st.Yacc, st.K * st.dp, st.xseq_base + 2u);
+            }
+            serial_finalize(st, 1, c.sRow, c.sRed);
+        });
         return;
     }
     mma_zero_tiles(c);
@@ -813,7 +822,14 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
         block_share(st, 0, blockIdx.x, G, nb, ne);
         if (nb < ne) { mma_stage_tile(c, st, st.list, nb, (int)min((long long)HMY_MT, ne - nb)); staged = nb; }
     }
-    grid_barrier(st, G, gen++);              // all Told sums are in
+    const bool multi = FUSED && st.xworld > 1;
+    unsigned int xs = st.xseq_base;
+    if (multi) {                             // all Told sums are in: sum them over the GPUs
+        ++xs;
+        grid_barrier_serial(st, G, gen++, c.sFlag, [&]() { xchg_allreduce<float>(st, st.Told, st.nblk * st.B * st.K, xs); });
+    } else {
+        grid_barrier(st, G, gen++);
+    }
     hmy_trace(st, 2);
     for (int blk = 0; blk < st.nblk; ++blk) {
         mma_update_tables(c, st, blk);
@@ -829,10 +845,23 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
             if (nb < ne) { mma_stage_tile(c, st, st.list, nb, (int)min((long long)HMY_MT, ne - nb)); staged = nb; }
         }
         if (blk + 1 < st.nblk) {
-            grid_barrier(st, G, gen++);
+            if (multi) {                     // the block's re-added batch sums, summed over the GPUs
+                ++xs;
+                grid_barrier_serial(st, G, gen++, c.sFlag, [&]() {
+                    xchg_allreduce<float>(st, st.Dnew + (size_t)blk * st.B * st.K, st.B * st.K, xs);
+                });
+            } else {
+                grid_barrier(st, G, gen++);
+            }
         } else {
             mma_flush_round_sums(c, st);
-            grid_barrier_serial(st, G, gen++, c.sFlag, [&]() { serial_finalize(st, 0, c.sRow, c.sRed); });
+            grid_barrier_serial(st, G, gen++, c.sFlag, [&]() {
+                if (multi) {
+                    xchg_allreduce<double>(st, st.obj, 4 + st.B * st.K, xs + 1u);
+                    xchg_allreduce<double>(st, st.Yacc, st.K * st.dp, xs + 2u);
+                }
+                serial_finalize(st, 0, c.sRow, c.sRed);
+            });
         }
         hmy_trace(st, 5 + 3 * blk);
     }

@@ -219,7 +219,9 @@ class Comm:
 
 def _cuda_engine_factory(problem, lo, hi, device_index, comm, options):
     eng = _cabi.Engine(device_index, hi - lo, problem.N, lo, problem.d, problem.K, problem.levels)
-    for k, v in (options or {}).items():
+    options = dict(options or {})
+    eng.want_fused = bool(options.pop("fused", 1))       # host-side switch, not a library option
+    for k, v in options.items():
         eng.set_option(k, v)
     if comm is not None and comm.world > 1:
         import torch
@@ -320,6 +322,18 @@ class Harmony:
         lamb = problem.lamb if not problem.lambda_estimation else None
         self._engine.set_params(problem.Pr_b, problem.theta, problem.sigma, lamb, problem.lambda_estimation,
                                 alpha, block_size)
+        if comm is not None and comm.world > 1 and getattr(self._engine, "want_fused", False):
+            # fused mode: the round kernel exchanges its K x B tables itself through peer-mapped
+            # memory; only the 64-byte IPC handles travel through torch.distributed
+            try:
+                mine = self._engine.comm_export()
+            except _cabi.EngineError:
+                mine = None                               # e.g. d > 64: stay in staged mode
+            handles = [None] * comm.world
+            comm.dist.all_gather_object(handles, mine, group=comm.group)
+            if all(h is not None for h in handles):
+                self._engine.comm_attach(comm.rank, comm.world, handles)
+            comm.dist.barrier(group=comm.group)
         self.allocate_buffers()
         if run:
             self.init_cluster(random_state, init_centroids)

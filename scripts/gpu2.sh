@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader
-timeout 900 python -m pytest tests/test_gpu_dist.py -x -q -s 2>&1 | tail -15
-for n in 1 2; do
+timeout 900 python -m pytest tests/test_gpu_dist.py -x -q -s 2>&1 | tail -25
+for n in 2; do
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_g$n.json 2> gpurun_out/bench_g$n.err; echo "bench $n exit $?"; tail -2 gpurun_out/bench_g$n.err
 python -c "import json; d=json.loads(open('gpurun_out/bench_g$n.json').read().strip().splitlines()[-1]); print($n, 'value', d['value'], 'ms/step', d['ms_per_step'], 'round ms', d['roofline']['avg_launch_ms'], 'e2e', d['e2e'] and d['e2e']['value'], d['config']['mode'])"
 done

@@ -16,7 +16,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, name):
+def _worker(rank, world, port, q, name, fused):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -30,16 +30,18 @@ def _worker(rank, world, port, q, name):
                        sigma=inp["sigma"], K=int(inp["K"]))
         ho = Harmony(prob, float(inp["alpha"]), int(inp["max_iter_harmony"]), int(inp["max_iter_kmeans"]),
                      float(inp["epsilon_kmeans"]), float(inp["epsilon_harmony"]), float(inp["block_size"]), False,
-                     int(inp["random_state"]), rank, comm=True, init_centroids=inp["Y0"])
+                     int(inp["random_state"]), rank, comm=True, init_centroids=inp["Y0"],
+                     engine_options={"fused": fused})
         Zc = ho.Z_corr                      # gathered over ranks
         q.put(dict(rank=rank, rounds=list(ho.kmeans_rounds), Z=Zc, obj=list(ho.objective_harmony),
-                   lo=ho._lo, hi=ho._hi))
+                   lo=ho._lo, hi=ho._hi, fused=ho._engine.counter("fused")))
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("name", ["synth", "pbmc"])
-def test_two_gpus_match_reference(name):
+def test_two_gpus_match_reference(name, fused):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -47,7 +49,7 @@ def test_two_gpus_match_reference(name):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, name)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, name, fused)) for r in range(2)]
     for p in procs:
         p.start()
     outs = sorted([q.get(timeout=600) for _ in procs], key=lambda o: o["rank"])
@@ -56,9 +58,10 @@ def test_two_gpus_match_reference(name):
         assert p.exitcode == 0
     inp, gold = load_case(name)
     a, b = outs
+    assert a["fused"] == b["fused"] == fused
     assert a["rounds"] == b["rounds"] == list(gold["kmeans_rounds"])
     np.testing.assert_array_equal(a["Z"], b["Z"])
     err = rel_max(a["Z"][gold["final_cells"]], gold["Zcorr_final"])
-    print(f"\n[{name}] 2-GPU staged mode: final Z_corr vs reference fp32 {err:.3e}")
+    print(f"\n[{name}] 2-GPU {"fused" if fused else "staged"} mode: final Z_corr vs reference fp32 {err:.3e}")
     assert err < 1e-4
     np.testing.assert_allclose(a["obj"], gold["objective_harmony"], rtol=5e-5)
