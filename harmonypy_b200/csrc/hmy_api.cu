@@ -66,7 +66,7 @@ struct hmy_ctx {
     hmy_allreduce_fn ar = nullptr; void* ar_user = nullptr;
     unsigned char* xbuf = nullptr; size_t xbytes = 0;      // this rank's exchange buffer
     std::vector<void*> xopened;                            // peers' buffers opened through IPC
-    bool fused = false;
+    bool fused = false, force_fused_kernel = false;
     unsigned int xseq = 0;
 };
 
@@ -210,7 +210,6 @@ static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_glob
         if (dev_alloc(ctx, &ctx->zero_ridge, ctx->zero_ridge_bytes)) return 1;
         st.Gram = (double*)ctx->zero_ridge; st.Mom = st.Gram + nG;
     }
-    if (dev_alloc(ctx, &st.Yacc, (size_t)K * st.dp)) return 1;
     CK(cudaMallocHost((void**)&ctx->h_obj, 4 * sizeof(double)));
     st.Yhat = ctx->Ybuf[0]; st.Ynext = ctx->Ybuf[1]; ctx->Ylast = ctx->Ybuf[0];
     CK(cudaMemset(ctx->Ybuf[0], 0, (size_t)K * st.dp * sizeof(float)));
@@ -281,12 +280,13 @@ static int plan_round(hmy_ctx* ctx) {
     ctx->G = nb * ctx->sms;
     // per-round zero block: Told | Dnew | Yacc is separate (ridge also uses it) | obj
     const size_t nT = (size_t)nblk * st.B * st.K;
-    ctx->zero_round_bytes = 2 * nT * sizeof(float) + (4 + (size_t)st.B * st.K) * sizeof(double);
+    ctx->zero_round_bytes = 2 * nT * sizeof(float) + (4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double);
     ctx->zero_round_bytes = (ctx->zero_round_bytes + 7) & ~(size_t)7;
     if (dev_alloc(ctx, &ctx->zero_round, ctx->zero_round_bytes + 8)) return 1;
     st.obj = (double*)ctx->zero_round;                      // 8-byte aligned at the front
     st.Ofresh = st.obj + 4;
-    st.Told = (float*)(st.Ofresh + (size_t)st.B * st.K); st.Dnew = st.Told + nT;
+    st.Yacc = st.Ofresh + (size_t)st.B * st.K;              // obj | Ofresh | Yacc: one exchange / all-reduce
+    st.Told = (float*)(st.Yacc + (size_t)st.K * st.dp); st.Dnew = st.Told + nT;
     if (dev_alloc(ctx, &st.blk_start, (size_t)nblk + 1)) return 1;
     ctx->list_chunks = 4 * ctx->sms;
     {
@@ -496,10 +496,10 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
     if (timer_begin(ctx, ctx->ev_init)) return 1;
     if (ctx->persistent && (!ctx->ar || ctx->fused)) {
         st.xseq_base = ctx->xseq;
-        if (ctx->fused) ctx->xseq += 2;
+        if (ctx->fused) ctx->xseq += 1;
         HmyDev s = st; int mode = 1; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, ctx->fused ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
+        if (launch(ctx, (ctx->fused || ctx->force_fused_kernel) ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
         ctx->gen += 1;
     } else {
         if (staged_round(ctx, 2, 0)) return 1;
@@ -544,10 +544,10 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
     if (timer_begin(ctx, ctx->ev_round)) return 1;
     if (ctx->persistent && (!ctx->ar || ctx->fused)) {
         st.xseq_base = ctx->xseq;
-        if (ctx->fused) ctx->xseq += (unsigned int)st.nblk + 2u;
+        if (ctx->fused) ctx->xseq += st.xrelaxed ? 1u : (unsigned int)st.nblk + 1u;
         HmyDev s = st; int mode = 0; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, ctx->fused ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
+        if (launch(ctx, (ctx->fused || ctx->force_fused_kernel) ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
         ctx->gen += (unsigned int)st.nblk + 1u;
     } else {
         const int64_t nT = (int64_t)st.nblk * st.B * st.K, BK = (int64_t)st.B * st.K;
@@ -707,6 +707,12 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
         }
         return 0;
     }
+    if (n == "force_fused_kernel") { ctx->force_fused_kernel = value != 0; return 0; }   // codegen A/B only
+    if (n == "relaxed") {
+        // fused multi-GPU mode only: 1 = the K x B table crosses GPUs once per round instead of once
+        // per block (Jacobi across GPUs, Gauss-Seidel inside a GPU; north_star's single exchange)
+        ctx->st.xrelaxed = value != 0; return 0;
+    }
     if (n == "ridge_mma") {
         if (ctx->have_params) FAIL("option ridge_mma must be set before hmy_set_params");
         ctx->want_ridge_mma = value != 0; return 0;
@@ -774,9 +780,8 @@ extern "C" int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B) {
     if (!handle_out_64B) FAIL("hmy_comm_export: NULL handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (!ctx->xbuf) {
-        size_t slot = (size_t)st.nblk * st.B * st.K * sizeof(float);
-        slot = std::max(slot, (size_t)(4 + (size_t)st.B * st.K) * sizeof(double));
-        slot = std::max(slot, (size_t)st.K * st.dp * sizeof(double));
+        size_t slot = (size_t)st.B * st.K * sizeof(float);
+        slot = std::max(slot, (size_t)(4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double));
         slot = (slot + 255) & ~(size_t)255;
         st.xslot = slot;
         ctx->xbytes = HMY_XPAYLOAD_OFF + 2 * (size_t)HMY_MAX_WORLD * slot;

@@ -64,6 +64,7 @@ struct HmyDev {
     // fused multi-GPU exchange: peer-mapped exchange buffers (own one included), see hmy_xchg.cuh
     unsigned char* xpeer[HMY_MAX_WORLD];
     int xrank, xworld;
+    int xrelaxed;                    // 1: exchange only at the end of a round (blocks see local updates only)
     unsigned int xseq_base;          // sequence number of the last exchange before this launch
     unsigned long long xslot;        // bytes of one payload slot
 };

@@ -299,18 +299,19 @@ __device__ void mma_flush_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk) {
 // (harmony.py:506-507), take block blk out (:491-492), E = rowsum x Pr_b (:388/:491),
 // P = clamp(E / clamp(O+E))^theta (:495-499).  Identical inputs and order on every CTA.
 template <int NT, int WN>
-__device__ void mma_update_tables(MmaCtx<NT, WN>& c, const HmyDev& st, int blk) {
+__device__ void mma_update_tables(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, bool combined) {
     constexpr int NTHR = 128 * WN;
     const int n = st.B * st.K, K = st.K, tid = threadIdx.x;
     const float* dn = st.Dnew + (size_t)(blk > 0 ? blk - 1 : 0) * n;
     const float* to = st.Told + (size_t)blk * n;
+    const bool use_told = !(combined && blk > 0);
     for (int i0 = tid; i0 < n; i0 += NTHR * 8) {
         float a[8], r[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * NTHR;
             a[u] = (i < n && blk > 0) ? __ldcg(&dn[i]) : 0.f;
-            r[u] = (i < n) ? __ldcg(&to[i]) : 0.f;
+            r[u] = (i < n && use_told) ? __ldcg(&to[i]) : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -775,16 +776,89 @@ __device__ __forceinline__ void mma_load_penalty(MmaCtx<NT, WN>& c, const HmyDev
 }
 
 // ---- kernels ---------------------------------------------------------------------------------
-// FUSED: exchange the K x B tables with the other GPUs inside the grid barriers (hmy_xchg.cuh);
-// a separate instantiation so that the single-GPU kernel carries none of that code.
+// ---- fused multi-GPU mode: a dedicated communication CTA ------------------------------------------
+// With more than one GPU the LAST CTA of the grid does no cell work: it waits until all worker
+// CTAs have arrived at a barrier, exchanges the K x B table with the other GPUs (hmy_xchg.cuh)
+// and releases the workers.  Keeping that code out of the worker path matters: inlined into the
+// worker's barrier it cost the 255-register kernel 40 % of its speed in spills.
+__device__ __forceinline__ void worker_barrier(const HmyDev& st, unsigned int gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(st.bar_count, 1u);
+        while ((int)(ld_acquire_u32(st.bar_gen) - gen) < 0) { __nanosleep(20); }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void comm_wait_workers(const HmyDev& st, unsigned int nworkers) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_u32(st.bar_count) < nworkers) { __nanosleep(20); }
+        *st.bar_count = 0u;
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void comm_release(const HmyDev& st, unsigned int gen) {
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); st_release_u32(st.bar_gen, gen); }
+}
+
+static __device__ __noinline__ void comm_cta_main(const HmyDev& st, int mode, unsigned int gen_base, unsigned int GW,
+                                           double* sRow, double* sRed) {
+    const int n = st.B * st.K, nend = 4 + n + st.K * st.dp;
+    unsigned int gen = gen_base + 1u, xs = st.xseq_base;
+    if (mode == 1) {
+        comm_wait_workers(st, GW);
+        xchg_allreduce<double>(st, st.obj, nend, ++xs);          // objective sums | Ofresh | Yacc
+        serial_finalize(st, 1, sRow, sRed);
+        comm_release(st, gen);
+        return;
+    }
+    const bool exact = !st.xrelaxed;
+    comm_wait_workers(st, GW);                                   // all local Told sums are in
+    if (exact) xchg_allreduce<float>(st, st.Told, n, ++xs);      // block 0's removed sums
+    comm_release(st, gen++);
+    for (int blk = 0; blk < st.nblk; ++blk) {
+        comm_wait_workers(st, GW);
+        if (blk + 1 < st.nblk) {
+            if (exact) {
+                // one K x B table per block: (re-added sums of blk) - (removed sums of blk + 1)
+                float* dnew = st.Dnew + (size_t)blk * n;
+                const float* told = st.Told + (size_t)(blk + 1) * n;
+                for (int i0 = threadIdx.x; i0 < n; i0 += 8 * blockDim.x) {
+                    float a[8], r[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; a[u] = (i < n) ? __ldcg(&dnew[i]) : 0.f; r[u] = (i < n) ? __ldcg(&told[i]) : 0.f; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) __stcg(&dnew[i], a[u] - r[u]); }
+                }
+                __syncthreads();
+                xchg_allreduce<float>(st, dnew, n, ++xs);
+            }
+        } else {
+            xchg_allreduce<double>(st, st.obj, nend, ++xs);
+            serial_finalize(st, 0, sRow, sRed);
+        }
+        comm_release(st, gen++);
+    }
+}
+
+// FUSED = true is the multi-GPU instantiation (the single-GPU kernel carries none of that code).
 template <int NT, int WN, bool FUSED>
 __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_round_mma(HmyDev st, int mode, unsigned int gen_base) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr int NTHR = 128 * WN;
+    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN, NT);
+    const bool multi_any = FUSED && st.xworld > 1;
+    const unsigned int G = multi_any ? gridDim.x - 1u : gridDim.x;          // worker CTAs
+    if (multi_any && blockIdx.x == G) {
+        double* sRow = (double*)(smem + p.off_misc);
+        comm_cta_main(st, mode, gen_base, G, sRow, sRow + 256);
+        return;
+    }
     MmaCtx<NT, WN> c;
     mma_ctx_init(c, st, smem);
-    const MmaSmem p = mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, st.nblk, WN, NT);
-    const unsigned int G = gridDim.x;
     const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G;
     hmy_trace(st, 0);
     mma_load_centroids(c, st);
@@ -794,13 +868,8 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
         __syncthreads();
         mma_process_block(c, st, 0, nullptr, c0, c1, true, -1);
         mma_flush_round_sums(c, st);
-        grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() {
-            if (FUSED && st.xworld > 1) {
-                xchg_allreduce<double>(st, st.obj, 4 + st.B * st.K, st.xseq_base + 1u);     // objective sums | Ofresh
-                xchg_allreduce<double>(st, st.Yacc, st.K * st.dp, st.xseq_base + 2u);
-            }
-            serial_finalize(st, 1, c.sRow, c.sRed);
-        });
+        if (multi_any) worker_barrier(st, gen_base + 1u);
+        else grid_barrier_serial(st, G, gen_base + 1u, c.sFlag, [&]() { serial_finalize(st, 1, c.sRow, c.sRed); });
         return;
     }
     mma_zero_tiles(c);
@@ -822,17 +891,12 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
         block_share(st, 0, blockIdx.x, G, nb, ne);
         if (nb < ne) { mma_stage_tile(c, st, st.list, nb, (int)min((long long)HMY_MT, ne - nb)); staged = nb; }
     }
-    const bool multi = FUSED && st.xworld > 1;
-    unsigned int xs = st.xseq_base;
-    if (multi) {                             // all Told sums are in: sum them over the GPUs
-        ++xs;
-        grid_barrier_serial(st, G, gen++, c.sFlag, [&]() { xchg_allreduce<float>(st, st.Told, st.nblk * st.B * st.K, xs); });
-    } else {
-        grid_barrier(st, G, gen++);
-    }
+    const bool multi = multi_any && !st.xrelaxed;      // exact mode: one table exchange per block
+    if (multi_any) worker_barrier(st, gen++);          // comm CTA: all Told sums are in (+ exchange)
+    else grid_barrier(st, G, gen++);
     hmy_trace(st, 2);
     for (int blk = 0; blk < st.nblk; ++blk) {
-        mma_update_tables(c, st, blk);
+        mma_update_tables(c, st, blk, multi);
         hmy_trace(st, 3 + 3 * blk);
         long long lb, le;
         block_share(st, blk, blockIdx.x, G, lb, le);
@@ -843,25 +907,12 @@ __global__ void __launch_bounds__(128 * WN, (WN == 2 && NT <= 8) ? 2 : 1) k_roun
             long long nb, ne;
             block_share(st, blk + 1, blockIdx.x, G, nb, ne);
             if (nb < ne) { mma_stage_tile(c, st, st.list, nb, (int)min((long long)HMY_MT, ne - nb)); staged = nb; }
-        }
-        if (blk + 1 < st.nblk) {
-            if (multi) {                     // the block's re-added batch sums, summed over the GPUs
-                ++xs;
-                grid_barrier_serial(st, G, gen++, c.sFlag, [&]() {
-                    xchg_allreduce<float>(st, st.Dnew + (size_t)blk * st.B * st.K, st.B * st.K, xs);
-                });
-            } else {
-                grid_barrier(st, G, gen++);
-            }
+            if (multi_any) worker_barrier(st, gen++);
+            else grid_barrier(st, G, gen++);
         } else {
             mma_flush_round_sums(c, st);
-            grid_barrier_serial(st, G, gen++, c.sFlag, [&]() {
-                if (multi) {
-                    xchg_allreduce<double>(st, st.obj, 4 + st.B * st.K, xs + 1u);
-                    xchg_allreduce<double>(st, st.Yacc, st.K * st.dp, xs + 2u);
-                }
-                serial_finalize(st, 0, c.sRow, c.sRed);
-            });
+            if (multi_any) worker_barrier(st, gen++);
+            else grid_barrier_serial(st, G, gen++, c.sFlag, [&]() { serial_finalize(st, 0, c.sRow, c.sRed); });
         }
         hmy_trace(st, 5 + 3 * blk);
     }

@@ -16,7 +16,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q, name, fused):
+def _worker(rank, world, port, q, name, fused, relaxed=0):
     import torch
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -31,7 +31,7 @@ def _worker(rank, world, port, q, name, fused):
         ho = Harmony(prob, float(inp["alpha"]), int(inp["max_iter_harmony"]), int(inp["max_iter_kmeans"]),
                      float(inp["epsilon_kmeans"]), float(inp["epsilon_harmony"]), float(inp["block_size"]), False,
                      int(inp["random_state"]), rank, comm=True, init_centroids=inp["Y0"],
-                     engine_options={"fused": fused})
+                     engine_options={"fused": fused, "relaxed": relaxed})
         Zc = ho.Z_corr                      # gathered over ranks
         q.put(dict(rank=rank, rounds=list(ho.kmeans_rounds), Z=Zc, obj=list(ho.objective_harmony),
                    lo=ho._lo, hi=ho._hi, fused=ho._engine.counter("fused")))
@@ -65,3 +65,28 @@ def test_two_gpus_match_reference(name, fused):
     print(f"\n[{name}] 2-GPU {"fused" if fused else "staged"} mode: final Z_corr vs reference fp32 {err:.3e}")
     assert err < 1e-4
     np.testing.assert_allclose(a["obj"], gold["objective_harmony"], rtol=5e-5)
+
+
+def test_two_gpus_relaxed_exchange_deviation():
+    """Fused mode with one exchange per round ('relaxed', what north_star sketches): not exact --
+    remote GPUs' block updates are one round stale -- so the deviation from the reference is
+    measured and bounded here instead of being gated at 1e-4."""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, "pbmc", 1, 1)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=600) for _ in procs], key=lambda o: o["rank"])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    inp, gold = load_case("pbmc")
+    err = rel_max(outs[0]["Z"][gold["final_cells"]], gold["Zcorr_final"])
+    print(f"\n[pbmc] 2-GPU fused RELAXED mode: final Z_corr vs reference fp32 {err:.3e}, rounds {outs[0]['rounds']}")
+    np.testing.assert_array_equal(outs[0]["Z"], outs[1]["Z"])
+    assert err < 5e-2
