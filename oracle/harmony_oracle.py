@@ -131,15 +131,17 @@ class HarmonyOracle:
         """Three-term objective (harmony.py:394-417)."""
         ft = self.ft
         c0 = 2000.0 / self.N                                   # :396
-        err = float(np.sum(self.R * self.dist))                # :399
+        # the three sums are accumulated in float64 (the values are `ft`): convergence is a 1e-5
+        # threshold on these sums and must not depend on NumPy's fp32 summation order
+        err = float(np.sum(self.R * self.dist, dtype=np.float64))                # :399
         with np.errstate(divide="ignore", invalid="ignore"):
             h = self.R * np.log(self.R)                        # :572-576
         h = np.where(np.isfinite(h), h, ft(0))
-        ent = float(np.sum(h * self.sigma[:, None]))           # :402
+        ent = float(np.sum(h * self.sigma[:, None], dtype=np.float64))           # :402
         Oc = np.maximum(self.O, ft(1e-8))                      # :407
         Ec = np.maximum(self.E, ft(1e-8))                      # :408
         tl = self.theta[None, :] * np.log((Oc + Ec) / Ec)      # :409-410
-        cross = float(np.sum((self.R * self.sigma[:, None]) * (tl @ self.Phi)))  # :405, :411
+        cross = float(np.sum((self.R * self.sigma[:, None]) * (tl @ self.Phi), dtype=np.float64))  # :405, :411
         self.objective_kmeans.append((err + ent + cross) * c0)
         self.objective_kmeans_dist.append(err * c0)
         self.objective_kmeans_entropy.append(ent * c0)
