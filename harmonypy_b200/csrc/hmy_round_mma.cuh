@@ -80,6 +80,10 @@ __host__ __device__ inline MmaSmem mma_smem_plan(int d, int K, int KS, int B, in
     return s;
 }
 
+// n / d for n < 2^24 and 1 <= d <= 256 with m = ceil(2^32 / d): one IMAD.HI instead of a division
+__host__ __device__ inline unsigned int hmy_magic(int d) { return (unsigned int)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); }
+__device__ __forceinline__ int hmy_div(int n, unsigned int magic) { return (int)__umulhi((unsigned int)n, magic); }
+
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
 
@@ -117,6 +121,7 @@ struct MmaCtx {
     int *sCell, *sCombo, *sLev;
     double *sRow, *sRed; int* sFlag;
     int ZSH, RSH, NTW, KT2, dt;         // dt = k16 steps over the PCs
+    unsigned int mg_dp4, mg_kp4, mg_K;  // magic divisors
     int n0;                             // first n-tile of this warp
     int ntw;                            // n-tiles this warp really has
     int run_combo;
@@ -141,6 +146,7 @@ __device__ __forceinline__ void mma_ctx_init(MmaCtx<NT, WN>& c, const HmyDev& st
     c.sRow = (double*)(smem + p.off_misc); c.sRed = c.sRow + 256; c.sFlag = (int*)(c.sRed + 8);
     c.ZSH = p.ZSH; c.RSH = p.RSH; c.NTW = p.NTW; c.KT2 = p.KT2;
     c.dt = (st.d + 15) >> 4;
+    c.mg_dp4 = hmy_magic(st.dp >> 2); c.mg_kp4 = hmy_magic(st.Kp >> 2); c.mg_K = hmy_magic(st.K);
     const int warp = threadIdx.x >> 5, nh = warp >> 2;
     c.n0 = nh * NT;
     c.ntw = NT;
@@ -301,38 +307,38 @@ __device__ void mma_flush_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk) {
 template <int NT, int WN>
 __device__ void mma_update_tables(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, bool combined) {
     constexpr int NTHR = 128 * WN;
-    const int n = st.B * st.K, K = st.K, tid = threadIdx.x;
+    const int n = st.B * st.K, K = st.K, B = st.B, tid = threadIdx.x;
     const float* dn = st.Dnew + (size_t)(blk > 0 ? blk - 1 : 0) * n;
     const float* to = st.Told + (size_t)blk * n;
-    const bool use_told = !(combined && blk > 0);
-    for (int i0 = tid; i0 < n; i0 += NTHR * 8) {
-        float a[8], r[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * NTHR;
-            a[u] = (i < n && blk > 0) ? __ldcg(&dn[i]) : 0.f;
-            r[u] = (i < n && use_told) ? __ldcg(&to[i]) : 0.f;
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = i0 + u * NTHR;
-            if (i < n) { const int b = i / K, k = i - b * K; c.Os[b * c.KT2 + k] += a[u] - r[u]; }
-        }
-    }
-    __syncthreads();
+    const bool use_told = !(combined && blk > 0), use_dn = blk > 0;
+    // thread k owns cluster k: one round trip for the whole column, row sum and penalty on the fly
     for (int k = tid; k < K; k += NTHR) {
         float rs = 0.f;
-        for (int b = 0; b < st.lev0; ++b) rs += c.Os[b * c.KT2 + k];
-        c.sRs[k] = rs;
-    }
-    __syncthreads();
-    for (int i = tid; i < n; i += NTHR) {
-        const int b = i / K, k = i - b * K;
-        const float o = c.Os[b * c.KT2 + k];
-        const float e = c.sRs[k] * c.sPrb[b];
-        const float ratio = fminf(fmaxf(e / fmaxf(o + e, 1e-8f), 1e-8f), 1.0f);
-        const float th = c.sTheta[b];
-        c.Ps[b * c.KT2 + k] = (th == 2.0f) ? ratio * ratio : powf(ratio, th);
+        for (int b0 = 0; b0 < B; b0 += 24) {
+            float a[24], r[24];
+#pragma unroll
+            for (int u = 0; u < 24; ++u) {
+                const int b = b0 + u;
+                a[u] = (b < B && use_dn) ? __ldcg(&dn[b * K + k]) : 0.f;
+                r[u] = (b < B && use_told) ? __ldcg(&to[b * K + k]) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 24; ++u) {
+                const int b = b0 + u;
+                if (b < B) {
+                    const float o = c.Os[b * c.KT2 + k] + (a[u] - r[u]);
+                    c.Os[b * c.KT2 + k] = o;
+                    if (b < st.lev0) rs += o;
+                }
+            }
+        }
+        for (int b = 0; b < B; ++b) {
+            const float o = c.Os[b * c.KT2 + k];
+            const float e = rs * c.sPrb[b];
+            const float ratio = fminf(fmaxf(e / fmaxf(o + e, 1e-8f), 1e-8f), 1.0f);
+            const float th = c.sTheta[b];
+            c.Ps[b * c.KT2 + k] = (th == 2.0f) ? ratio * ratio : powf(ratio, th);
+        }
     }
     __syncthreads();
 }
@@ -349,7 +355,7 @@ __device__ void mma_load_O(MmaCtx<NT, WN>& c, const HmyDev& st) {
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * NTHR;
-            if (i < n) { const int b = i / K, k = i - b * K; c.Os[b * c.KT2 + k] = (float)o[u]; }
+            if (i < n) { const int b = hmy_div(i, c.mg_K), k = i - b * K; c.Os[b * c.KT2 + k] = (float)o[u]; }
         }
     }
 }
@@ -398,7 +404,7 @@ __device__ void mma_phase0(MmaCtx<NT, WN>& c, const HmyDev& st, long long c0, lo
                 for (int u = 0; u < RU; ++u) {
                     const int i = tid + u * NTHR;
                     if (i < total) {
-                        const int row = i / Kp4, c4 = i - row * Kp4;
+                        const int row = hmy_div(i, c.mg_kp4), c4 = i - row * Kp4;
                         uint2 hi, lo;
                         split2(v[u].x * HMY_OPSCALE, v[u].y * HMY_OPSCALE, hi.x, lo.x);
                         split2(v[u].z * HMY_OPSCALE, v[u].w * HMY_OPSCALE, hi.y, lo.y);
@@ -500,7 +506,7 @@ __device__ void mma_stage_tile(MmaCtx<NT, WN>& c, const HmyDev& st, const int* l
                 for (int u = 0; u < ZU; ++u) {
                     const int i = base + tid + u * NTHR;
                     if (i < total) {
-                        const int row = i / dp4, c4 = i - row * dp4;
+                        const int row = hmy_div(i, c.mg_dp4), c4 = i - row * dp4;
                         zr[u] = __ldg(reinterpret_cast<const float4*>(st.Zcos + (size_t)c.sCell[row] * dp) + c4);
                     }
                 }
@@ -508,7 +514,7 @@ __device__ void mma_stage_tile(MmaCtx<NT, WN>& c, const HmyDev& st, const int* l
                 for (int u = 0; u < ZU; ++u) {
                     const int i = base + tid + u * NTHR;
                     if (i < total) {
-                        const int row = i / dp4, c4 = i - row * dp4;
+                        const int row = hmy_div(i, c.mg_dp4), c4 = i - row * dp4;
                         uint2 hi, lo;
                         split2(zr[u].x * HMY_OPSCALE, zr[u].y * HMY_OPSCALE, hi.x, lo.x);
                         split2(zr[u].z * HMY_OPSCALE, zr[u].w * HMY_OPSCALE, hi.y, lo.y);
@@ -672,8 +678,8 @@ __device__ void mma_process_block(MmaCtx<NT, WN>& c, const HmyDev& st, int blk, 
             int r = row0;
             while (r < rhi) {
                 const int cb = c.sCombo[r];
-                int e = r + 1;
-                while (e < rhi && c.sCombo[e] == cb) ++e;
+                int e = rhi;
+                if (c.sCombo[rhi - 1] != cb) { e = r + 1; while (e < rhi && c.sCombo[e] == cb) ++e; }
                 if (cb != c.run_combo) { mma_end_run(c, st, blk); c.run_combo = cb; }
                 const bool in0 = (row0 + g) >= r && (row0 + g) < e, in1 = (row0 + g + 8) >= r && (row0 + g + 8) < e;
 #pragma unroll
