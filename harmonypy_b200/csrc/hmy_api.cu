@@ -9,6 +9,8 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <chrono>
+#include <cstdlib>
 
 #define HMY_NONTEMPLATE_KERNELS 1
 #include "../../include/harmony_b200.h"
@@ -56,6 +58,8 @@ struct hmy_ctx {
     long long* d_perm = nullptr;
     int* d_cnt = nullptr; int list_chunks = 0;
     float* d_tmp = nullptr; size_t tmp_bytes = 0;
+    unsigned char* h_stage[2] = {nullptr, nullptr};      // pinned bounce buffers for result reads
+    cudaEvent_t ev_stage[2] = {nullptr, nullptr};
     double* h_obj = nullptr;     // pinned
     // counters / timers
     long long launches = 0, rounds = 0, ridge_passes = 0;
@@ -247,6 +251,7 @@ extern "C" void hmy_destroy(hmy_ctx* ctx) {
     if (ctx->d_perm) cudaFree(ctx->d_perm);
     if (ctx->d_tmp) cudaFree(ctx->d_tmp);
     if (ctx->h_obj) cudaFreeHost(ctx->h_obj);
+    for (int i = 0; i < 2; ++i) { if (ctx->h_stage[i]) cudaFreeHost(ctx->h_stage[i]); if (ctx->ev_stage[i]) cudaEventDestroy(ctx->ev_stage[i]); }
     for (auto& e : ctx->ev_round) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ctx->ev_ridge) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ctx->ev_init) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -337,6 +342,14 @@ extern "C" int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* thet
 extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* codes_host) {
     HmyDev& st = ctx->st;
     CK(cudaSetDevice(ctx->device));
+    const bool tm = std::getenv("HMY_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!tm) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hmy_set_data] %-28s %7.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     if (!Z_host || !codes_host) FAIL("hmy_set_data: NULL input");
     const long long N = st.N; const int V = st.V;
     // combination key of every cell (covariate 0 most significant)
@@ -356,9 +369,23 @@ extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* co
             key[n] = k;
         }
     }
+    // stable sort of the cells by combination key: counting sort when the key range is small
+    // (the usual case: a handful of batch covariates), comparison sort otherwise
     std::vector<int> order((size_t)N);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+    {
+        unsigned long long kmax = 0;
+        for (long long n = 0; n < N; ++n) kmax = std::max(kmax, key[n]);
+        if (kmax < (1ull << 22)) {
+            std::vector<long long> cnt((size_t)kmax + 2, 0);
+            for (long long n = 0; n < N; ++n) cnt[key[n] + 1]++;
+            for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+            for (long long n = 0; n < N; ++n) order[(size_t)cnt[key[n]]++] = (int)n;
+        } else {
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+        }
+    }
+    lap("keys + counting sort");
     std::vector<int> pos_of((size_t)N), combo((size_t)N), combo_lev;
     std::vector<long long> combo_start;
     int ncombo = 0;
@@ -374,6 +401,7 @@ extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* co
     }
     combo_start.push_back(N);
     st.ncombo = ncombo;
+    lap("pos_of / combo tables");
     // ridge work items: <= HMY_SEG_MAX consecutive cells of one combination
     std::vector<int> seg;
     for (int c = 0; c < ncombo; ++c)
@@ -390,26 +418,29 @@ extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* co
     CK(cudaMemcpy(st.combo, combo.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(st.order, order.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(st.pos_of, pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-    {   // scale of the fp16 split of Z_orig in the tensor-core ridge passes: hi part below 2^14
-        float zm = 0.f;
-        const size_t nz = (size_t)N * st.d;
-        for (size_t i = 0; i < nz; ++i) { const float a = std::fabs(Z_host[i]); if (a > zm && std::isfinite(a)) zm = a; }
-        int e = 0; std::frexp(std::max(zm, 1e-30f), &e);
-        ctx->zscale = std::ldexp(1.0f, 13 - e);
-    }
+    lap("small uploads");
+    lap("max |Z|");
     // raw rows -> sorted padded layout + Z_cos
     float* raw = nullptr;
     CK(cudaMalloc((void**)&raw, (size_t)N * st.d * sizeof(float)));
     cudaError_t e = cudaMemcpyAsync(raw, Z_host, (size_t)N * st.d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) {
         const long long threads = N * 32;
-        k_ingest<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(st, raw);
+        cudaMemsetAsync(st.wmax, 0, sizeof(float), ctx->stream);        // borrowed as the |z| maximum
+        k_ingest<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(st, raw, st.wmax);
         ctx->launches++;
         e = cudaGetLastError();
     }
+    float zm = 0.f;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&zm, st.wmax, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    {   // scale of the fp16 split of Z_orig in the tensor-core ridge passes: hi part below 2^14
+        int ex = 0; std::frexp(std::max(zm, 1e-30f), &ex);
+        ctx->zscale = std::ldexp(1.0f, 13 - ex);
+    }
     cudaFree(raw);
     CK(e);
+    lap("malloc + H2D + ingest + free");
     ctx->have_data = true;
     return 0;
 }
@@ -625,8 +656,27 @@ static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_o
     k_unsort_rows<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(src, sp, ctx->d_tmp, w, st.order, st.N);
     ctx->launches++;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(host_out, ctx->d_tmp, need, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    // device -> pinned bounce buffer -> caller's (pageable, usually untouched) array, double buffered:
+    // the DMA of chunk i+1 overlaps the host copy (and first-touch page faults) of chunk i
+    constexpr size_t CHUNK = 16u << 20;
+    if (!ctx->h_stage[0]) {
+        for (int i = 0; i < 2; ++i) { CK(cudaMallocHost((void**)&ctx->h_stage[i], CHUNK)); CK(cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming)); }
+    }
+    const unsigned char* src8 = reinterpret_cast<const unsigned char*>(ctx->d_tmp);
+    unsigned char* dst8 = reinterpret_cast<unsigned char*>(host_out);
+    const size_t nchunk = (need + CHUNK - 1) / CHUNK;
+    for (size_t i = 0; i <= nchunk; ++i) {
+        if (i < nchunk) {
+            const size_t off = i * CHUNK, len = std::min(CHUNK, need - off);
+            CK(cudaMemcpyAsync(ctx->h_stage[i & 1], src8 + off, len, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaEventRecord(ctx->ev_stage[i & 1], ctx->stream));
+        }
+        if (i > 0) {
+            const size_t j = i - 1, off = j * CHUNK, len = std::min(CHUNK, need - off);
+            CK(cudaEventSynchronize(ctx->ev_stage[j & 1]));
+            std::memcpy(dst8 + off, ctx->h_stage[j & 1], len);
+        }
+    }
     return 0;
 }
 

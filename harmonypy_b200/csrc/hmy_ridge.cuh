@@ -318,13 +318,17 @@ __global__ void __launch_bounds__(HMY_THREADS) k_ridge_apply(HmyDev st) {
 #ifdef HMY_NONTEMPLATE_KERNELS
 // ---- ingest / egress ----------------------------------------------------------------------
 // one warp per cell: gather the caller's row into the sorted, padded layout; Z_cos (harmony.py:238)
-__global__ void k_ingest(HmyDev st, const float* Zraw) {
+__global__ void k_ingest(HmyDev st, const float* Zraw, float* zmax) {
     const long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (p >= st.N) return;
     const float* src = Zraw + (size_t)st.order[p] * st.d;
-    float ss = 0.f;
-    for (int j = lane; j < st.d; j += 32) { const float z = src[j]; ss += z * z; }
+    float ss = 0.f, zm = 0.f;
+    for (int j = lane; j < st.d; j += 32) { const float z = src[j]; ss += z * z; if (isfinite(z)) zm = fmaxf(zm, fabsf(z)); }
+    // largest |z| of the upload (scale of the fp16 split in the tensor-core ridge passes)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) zm = fmaxf(zm, __shfl_xor_sync(0xffffffffu, zm, o));
+    if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(zmax), __float_as_uint(zm));
     ss = warp_sum(ss);
     const float nrm = sqrtf(ss);
     for (int j = lane; j < st.dp; j += 32) {

@@ -40,18 +40,19 @@ __device__ __forceinline__ void ridge_tile_to_half(const float* src, int ld4, in
                                                    __half* Th, __half* Tl, int SH) {
     const float4* s4 = reinterpret_cast<const float4*>(src);
     const int total = nt * n4;
+    const unsigned int mg = hmy_magic(n4);
     for (int i0 = threadIdx.x; i0 < total; i0 += 8 * NTHR) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * NTHR;
-            if (i < total) { const int row = i / n4, c4 = i - row * n4; v[u] = __ldg(s4 + (size_t)row * ld4 + c4); }
+            if (i < total) { const int row = hmy_div(i, mg), c4 = i - row * n4; v[u] = __ldg(s4 + (size_t)row * ld4 + c4); }
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             const int i = i0 + u * NTHR;
             if (i < total) {
-                const int row = i / n4, c4 = i - row * n4;
+                const int row = hmy_div(i, mg), c4 = i - row * n4;
                 uint2 hi, lo;
                 split2(v[u].x * scale, v[u].y * scale, hi.x, lo.x);
                 split2(v[u].z * scale, v[u].w * scale, hi.y, lo.y);

@@ -81,8 +81,9 @@ __host__ __device__ inline MmaSmem mma_smem_plan(int d, int K, int KS, int B, in
 }
 
 // n / d for n < 2^24 and 1 <= d <= 256 with m = ceil(2^32 / d): one IMAD.HI instead of a division
-__host__ __device__ inline unsigned int hmy_magic(int d) { return (unsigned int)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); }
-__device__ __forceinline__ int hmy_div(int n, unsigned int magic) { return (int)__umulhi((unsigned int)n, magic); }
+// (d = 1 has no 32-bit magic: encoded as 0 and handled by the select)
+__host__ __device__ inline unsigned int hmy_magic(int d) { return d <= 1 ? 0u : (unsigned int)((0x100000000ull + (unsigned long long)d - 1ull) / (unsigned long long)d); }
+__device__ __forceinline__ int hmy_div(int n, unsigned int magic) { return magic ? (int)__umulhi((unsigned int)n, magic) : n; }
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
