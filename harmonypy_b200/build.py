@@ -73,7 +73,7 @@ def build(force=False, jobs=None, verbose=True):
         print(f"[harmonypy_b200.build] compiling {len(work)} objects for sm_100a with {jobs} jobs", flush=True)
     with ThreadPoolExecutor(jobs) as ex:
         objs = list(ex.map(_compile, work))
-    cmd = [_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [_nvcc(), *ARCH, "-shared", "-o", LIB, *objs, "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

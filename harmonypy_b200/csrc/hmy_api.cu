@@ -9,6 +9,7 @@
 #include <numeric>
 #include <string>
 #include <vector>
+#include <thread>
 #include <chrono>
 #include <cstdlib>
 
@@ -674,7 +675,20 @@ static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_o
         if (i > 0) {
             const size_t j = i - 1, off = j * CHUNK, len = std::min(CHUNK, need - off);
             CK(cudaEventSynchronize(ctx->ev_stage[j & 1]));
-            std::memcpy(dst8 + off, ctx->h_stage[j & 1], len);
+            // the destination is usually a fresh (never touched) array: its first-touch page faults
+            // dominate, so the copy is spread over a few host threads
+            const int nthr = (len >= (4u << 20)) ? 4 : 1;
+            if (nthr == 1) {
+                std::memcpy(dst8 + off, ctx->h_stage[j & 1], len);
+            } else {
+                std::thread th[4];
+                const size_t part = ((len / nthr) + 4095) & ~(size_t)4095;
+                for (int t = 0; t < nthr; ++t) {
+                    const size_t o2 = std::min(len, (size_t)t * part), l2 = std::min(part, len - o2);
+                    th[t] = std::thread([=]() { if (l2) std::memcpy(dst8 + off + o2, ctx->h_stage[j & 1] + o2, l2); });
+                }
+                for (int t = 0; t < nthr; ++t) th[t].join();
+            }
         }
     }
     return 0;
