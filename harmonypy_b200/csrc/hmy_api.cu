@@ -294,7 +294,7 @@ static int plan_round(hmy_ctx* ctx) {
     st.Yacc = st.Ofresh + (size_t)st.B * st.K;              // obj | Ofresh | Yacc: one exchange / all-reduce
     st.Told = (float*)(st.Yacc + (size_t)st.K * st.dp); st.Dnew = st.Told + nT;
     if (dev_alloc(ctx, &st.blk_start, (size_t)nblk + 1)) return 1;
-    ctx->list_chunks = 4 * ctx->sms;
+    ctx->list_chunks = std::min(4 * ctx->sms, 32 * HMY_SCAN_PER_LANE);
     {
         const size_t sm = ((size_t)nblk * HMY_LIST_THREADS + nblk) * sizeof(unsigned int);
         if (sm > 200 * 1024) FAIL("block_size gives too many blocks for the list builder");
@@ -523,8 +523,7 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
     }
     CK(cudaMemcpyAsync(st.Yhat, Y.data(), Y.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));          // Y is a stack-lifetime host buffer
-    CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
-    CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));     // obj | Ofresh | Yacc | Told | Dnew
     if (timer_begin(ctx, ctx->ev_init)) return 1;
     if (ctx->persistent && (!ctx->ar || ctx->fused)) {
         st.xseq_base = ctx->xseq;
@@ -566,13 +565,12 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
     {   // per-block cell lists (stable counting sort over position chunks)
         const size_t sm = ((size_t)st.nblk * HMY_LIST_THREADS + st.nblk) * sizeof(unsigned int);
         k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(st, ctx->d_cnt, 1);
-        k_block_scan<<<1, 256, 0, ctx->stream>>>(st, ctx->d_cnt, ctx->list_chunks);
+        k_block_scan<<<1, 32 * std::min(32, st.nblk), 0, ctx->stream>>>(st, ctx->d_cnt, ctx->list_chunks);
         k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(st, ctx->d_cnt, 0);
         ctx->launches += 3;
         CK(cudaGetLastError());
     }
-    CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));
-    CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
+    CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));     // obj | Ofresh | Yacc | Told | Dnew
     if (timer_begin(ctx, ctx->ev_round)) return 1;
     if (ctx->persistent && (!ctx->ar || ctx->fused)) {
         st.xseq_base = ctx->xseq;
