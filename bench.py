@@ -233,6 +233,39 @@ def run_reference(args, w):
     print(json.dumps(out), flush=True)
 
 
+def golden_parity(device_index):
+    """Second half of the metric: Z_corr max|d|/max|Z| vs the REFERENCE's stored output on the
+    bundled datasets (fixtures under tests/golden, generated from the real harmonypy), through the
+    public class with the reference permutation stream.  A few seconds; rank 0 only."""
+    from harmonypy_b200.harmony import Harmony, Problem
+    out = {"tolerance": 1e-4, "norm": "max|Z - Z_ref| / max|Z_ref|"}
+    for name, label in (("pbmc", "pbmc_3500"), ("ircolitis", "ircolitis_blood_cd8")):
+        try:
+            inp = np.load(os.path.join(ROOT, "tests", "golden", f"{name}_input.npz"))
+            gold = np.load(os.path.join(ROOT, "tests", "golden", f"{name}_golden.npz"))
+        except Exception:
+            continue
+        prob = Problem(Z=inp["Z"], codes=inp["codes"], levels=inp["levels"], level_names=[], Pr_b=inp["Pr_b"],
+                       theta=inp["theta"], lamb=inp["lamb"], lambda_estimation=bool(inp["lambda_estimation"]),
+                       sigma=inp["sigma"], K=int(inp["K"]))
+        t0 = time.perf_counter()
+        ho = Harmony(prob, float(inp["alpha"]), int(inp["max_iter_harmony"]), int(inp["max_iter_kmeans"]),
+                     float(inp["epsilon_kmeans"]), float(inp["epsilon_harmony"]), float(inp["block_size"]), False,
+                     int(inp["random_state"]), device_index, init_centroids=inp["Y0"])
+        Zc = ho.Z_corr
+        dt = time.perf_counter() - t0
+        ref, ref64 = gold["Zcorr_final"], gold["Zcorr_final_f64"]
+        cells = gold["final_cells"]
+        out[label] = {
+            "vs_reference_fp32": float(np.abs(Zc[cells] - ref).max() / np.abs(ref).max()),
+            "vs_reference_fp64_arbiter": float(np.abs(Zc[cells] - ref64).max() / np.abs(ref64).max()),
+            "kmeans_rounds_equal": list(map(int, ho.kmeans_rounds)) == list(map(int, gold["kmeans_rounds"])),
+            "cells": int(Zc.shape[0]), "seconds_incl_upload": dt,
+        }
+        del ho
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args, w):
     import torch
@@ -368,6 +401,9 @@ def run_ours(args, w):
                "sample": f"oracle/harmony_oracle.py (NumPy fp32 port of harmony.py) on the first {args.cpu_sample} "
                          f"cells of the workload, init assignment + harmonize to convergence, rounds {info['rounds']}"}
 
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = golden_parity(local_rank)
     if rank == 0:
         out = {
             "metric": "cells/sec to convergence (full Harmony loop)", "value": value, "unit": "cells/s",
@@ -384,7 +420,7 @@ def run_ours(args, w):
                                 else "staged launches" if args.staged else "persistent round kernel")},
             "cell_rounds_per_s": n_local * world * n_rounds / (ms_round / 1e3) if ms_round > 0 else None,
             "ridge_passes_per_s": n_local * world * n_ridge / (ms_ridge / 1e3) if ms_ridge > 0 else None,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),
             "clocks": clocks.summary(), "setup_seconds": t_setup,
         }
         print(json.dumps(out), flush=True)
@@ -404,6 +440,7 @@ def main():
     ap.add_argument("--staged", action="store_true", help="one launch per block step instead of the persistent kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--engine-opt", action="append", default=[], help="name=int engine option (debug / A-B runs)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

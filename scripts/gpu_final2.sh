@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -2
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err; echo "bench exit $?"; tail -2 gpurun_out/bench_ours.err
 for wl in syn10m8 syn5m8; do
