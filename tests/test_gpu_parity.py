@@ -119,6 +119,8 @@ def _oracle_for(prob, dtype=np.float64, **kw):
     (5000, 13, [3], 17, dict(theta=0.7, lamb=[0.3])),
     (3001, 64, [2, 2, 3], 33, dict(theta=[1.0, 2.0, 0.5], lamb=-1)),
     (257, 4, [2], 5, {}),                         # tiny: fewer cells than CTAs
+    (6000, 72, [3, 2], 40, {}),                   # d > 64: fp32 SIMT round + ridge kernels (fallback path)
+    (4000, 64, [4], 130, {}),                     # d = 64: tensor-core round, SIMT ridge (no spare PC column); K > 128
 ])
 def test_one_iteration_against_fp64_oracle(N, d, levels, K, kw):
     """init + 3 rounds + ridge on fresh synthetic data, every stage against the fp64 oracle."""
