@@ -846,7 +846,9 @@ extern "C" int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B) {
         slot = std::max(slot, (size_t)(4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double));
         slot = (slot + 255) & ~(size_t)255;
         st.xslot = slot;
-        ctx->xbytes = HMY_XPAYLOAD_OFF + 2 * (size_t)HMY_MAX_WORLD * slot;
+        st.xll_count = st.B * st.K;
+        ctx->xbytes = HMY_XPAYLOAD_OFF + 2 * (size_t)HMY_MAX_WORLD * slot
+                    + 2 * (size_t)HMY_MAX_WORLD * (size_t)st.xll_count * sizeof(uint2);
         CK(cudaMalloc((void**)&ctx->xbuf, ctx->xbytes));
         CK(cudaMemset(ctx->xbuf, 0, ctx->xbytes));
     }

@@ -66,7 +66,8 @@ struct HmyDev {
     int xrank, xworld;
     int xrelaxed;                    // 1: exchange only at the end of a round (blocks see local updates only)
     unsigned int xseq_base;          // sequence number of the last exchange before this launch
-    unsigned long long xslot;        // bytes of one payload slot
+    unsigned long long xslot;        // bytes of one payload slot (fenced protocol)
+    int xll_count;                   // elements of one low-latency slot (K x B)
 };
 
 __device__ __forceinline__ void hmy_trace(const HmyDev& st, int slot) {

@@ -824,7 +824,7 @@ static __device__ __noinline__ void comm_cta_main(const HmyDev& st, int mode, un
     }
     const bool exact = !st.xrelaxed;
     comm_wait_workers(st, GW);                                   // all local Told sums are in
-    if (exact) xchg_allreduce<float>(st, st.Told, n, ++xs);      // block 0's removed sums
+    if (exact) xchg_allreduce_ll_f32(st, st.Told, n, ++xs);      // block 0's removed sums
     comm_release(st, gen++);
     for (int blk = 0; blk < st.nblk; ++blk) {
         comm_wait_workers(st, GW);
@@ -841,7 +841,7 @@ static __device__ __noinline__ void comm_cta_main(const HmyDev& st, int mode, un
                     for (int u = 0; u < 8; ++u) { const int i = i0 + u * blockDim.x; if (i < n) __stcg(&dnew[i], a[u] - r[u]); }
                 }
                 __syncthreads();
-                xchg_allreduce<float>(st, dnew, n, ++xs);
+                xchg_allreduce_ll_f32(st, dnew, n, ++xs);
             }
         } else {
             xchg_allreduce<double>(st, st.obj, nend, ++xs);

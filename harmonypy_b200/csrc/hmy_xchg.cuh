@@ -100,3 +100,50 @@ __device__ __noinline__ void xchg_allreduce(const HmyDev& st, T* table, int coun
     }
     __syncthreads();
 }
+
+// ---- low-latency variant for the per-block K x B float tables ------------------------------------
+// LL protocol (as in NCCL's LL): every element travels as one 8-byte store {value, seq}; an 8-byte
+// store is atomic, so the receiver polls the payload itself -- no system-scope fence and no separate
+// flag round trip between "data written" and "data visible".  Twice the bytes, which is irrelevant
+// for 8-27 KB tables.  Slot layout: payload_ll[parity][source][count] of uint2, placed after the
+// fenced-protocol slots (see hmy_comm_export).  The two parities make a slot reusable: a rank can be
+// at most one exchange ahead of the slowest reader of the previous use of that parity.
+__device__ __forceinline__ void st_volatile_v2(uint2* p, unsigned int a, unsigned int b) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p) {
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+static __device__ __noinline__ void xchg_allreduce_ll_f32(const HmyDev& st, float* table, int count, unsigned int seq) {
+    const int W = st.xworld, me = st.xrank, tid = threadIdx.x, nth = blockDim.x;
+    const size_t ll_base = HMY_XPAYLOAD_OFF + 2 * (size_t)HMY_MAX_WORLD * st.xslot;
+    const size_t slot = (size_t)st.xll_count * sizeof(uint2);
+    const size_t my_off = ll_base + ((size_t)(seq & 1u) * HMY_MAX_WORLD + me) * slot;
+    // push {value, seq} to every rank (own copy included: the reduction reads all sources alike)
+    for (int i0 = tid; i0 < count; i0 += 8 * nth) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int i = i0 + u * nth; v[u] = (i < count) ? __ldcg(&table[i]) : 0.f; }
+        for (int r = 0; r < W; ++r) {
+            uint2* dst = reinterpret_cast<uint2*>(st.xpeer[r] + my_off);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { const int i = i0 + u * nth; if (i < count) st_volatile_v2(dst + i, __float_as_uint(v[u]), seq); }
+        }
+    }
+    // receive: poll each element of each source until it carries this sequence number
+    const unsigned char* mine = st.xpeer[me] + ll_base + (size_t)(seq & 1u) * HMY_MAX_WORLD * slot;
+    for (int i = tid; i < count; i += nth) {
+        float s = 0.f;
+        for (int r = 0; r < W; ++r) {
+            const uint2* src = reinterpret_cast<const uint2*>(mine + (size_t)r * slot) + i;
+            uint2 v = ld_volatile_v2(src);
+            while (v.y != seq) { __nanosleep(20); v = ld_volatile_v2(src); }
+            s += __uint_as_float(v.x);
+        }
+        __stcg(&table[i], s);
+    }
+    __syncthreads();
+}
