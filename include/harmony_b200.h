@@ -90,13 +90,23 @@ int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes);
 
 int hmy_synchronize(hmy_ctx* ctx);
 
-/* Options: "persistent" (0/1: one cooperative kernel per round vs one launch per block
- * step), "seed" (device permutation seed), "tile_mode", ...  Unknown names fail. */
+/* Options (unknown names fail):
+ *   "persistent" 0/1   one cooperative kernel per round (default) vs one launch per block step
+ *   "seed"       int   seed of the device-side permutation (perm_host == NULL)
+ *   "mma"        0/1   tensor-core round kernels (default, d <= 64) vs fp32 SIMT; before hmy_set_params
+ *   "ridge_mma"  0/1   tensor-core ridge passes (default, d <= 63) vs fp32 SIMT; before hmy_set_params
+ *   "mma_wn"     0/2   force two warps along the cluster axis (A/B runs); before hmy_set_params
+ *   "relaxed"    0/1   fused multi-GPU mode: exchange the K x B table once per round instead of once
+ *                      per block (NOT exact; default 0)
+ *   "timing"     0/1   CUDA-event timers around the stages (default 1)
+ *   "reset"      1     back to the state right after hmy_set_data (benchmark restarts)
+ *   "trace"      1     per-CTA timeline of the round kernel, read with hmy_get(HMY_TRACE) */
 int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value);
 
 /* Counters: "launches" (kernels launched by this library since creation), "rounds",
- * "ridge_passes".  Timers (CUDA events on the context stream, milliseconds, cumulative):
- * "ms_round", "ms_ridge".  Unknown names return -1. */
+ * "ridge_passes", "grid", "nblk", "ncombo", "mma", "ridge_mma", "fused", "round_threads",
+ * "smem_round".  Timers (CUDA events on the context stream, milliseconds, cumulative):
+ * "ms_round", "ms_ridge", "ms_init".  Unknown names return -1. */
 int64_t hmy_counter(const hmy_ctx* ctx, const char* name);
 double hmy_timer_ms(hmy_ctx* ctx, const char* name);
 

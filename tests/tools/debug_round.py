@@ -1,6 +1,6 @@
 import sys, os
 import numpy as np, pandas as pd
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from harmonypy_b200.harmony import Harmony, prepare_problem
 from harmonypy_b200.synthetic import make_synthetic
 from oracle.harmony_oracle import HarmonyOracle, onehot_from_codes, torch_perm_source
