@@ -23,6 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 INSTANCES = [(k, j) for k in (1, 2, 4, 8) for j in (4, 8, 16)]
 MMA_INSTANCES = [(4, 1), (8, 1), (14, 1), (16, 1), (8, 2), (14, 2), (16, 2)]
+TC5_INSTANCES = [4, 7, 8]          # 16-cluster column chunks of the tensor-memory round kernel (option "tc5")
 
 
 def _nvcc():
@@ -68,6 +69,9 @@ def build(force=False, jobs=None, verbose=True):
     for nt, wn in MMA_INSTANCES:
         work.append((os.path.join(CSRC, "hmy_inst_mma.cu"), os.path.join(OBJ, f"hmy_inst_mma_{nt}_{wn}.o"),
                      [f"-DHMY_NT={nt}", f"-DHMY_WN={wn}"]))
+    for nc in TC5_INSTANCES:
+        work.append((os.path.join(CSRC, "hmy_inst_tc5.cu"), os.path.join(OBJ, f"hmy_inst_tc5_{nc}.o"),
+                     [f"-DHMY_TC5_NC={nc}"]))
     jobs = jobs or min(len(work), os.cpu_count() or 4)
     if verbose:
         print(f"[harmonypy_b200.build] compiling {len(work)} objects for sm_100a with {jobs} jobs", flush=True)

@@ -18,6 +18,7 @@
 #include "hmy_common.cuh"
 #include "hmy_round.cuh"
 #include "hmy_round_mma.cuh"
+#include "hmy_round_tc5.cuh"
 #include "hmy_ridge.cuh"
 #include "hmy_ridge_mma.cuh"
 
@@ -38,6 +39,10 @@ struct hmy_ctx {
     bool use_mma = false, want_mma = true, ridge_mma = false, want_ridge_mma = true;
     float zscale = 1.f;
     int force_wn = 0;
+    // opt-in tcgen05 / tensor-memory round kernel (hmy_round_tc5.cuh)
+    bool want_tc5 = false, use_tc5 = false;
+    int tc5_nc = 0, smem_tc5 = 0, G_tc5 = 0;
+    const void* fn_tc5 = nullptr; const void* fn_tc5_fused = nullptr;
     int G = 0, sms = 0;
     int smem_round = 0, smem_mom = 0, smem_apply = 0, smem_solve = 0;
     int grid_ridge = 0, grid_mom = 0, ridge_threads = HMY_THREADS;
@@ -109,6 +114,10 @@ HMY_DECL_BIND(8, 4) HMY_DECL_BIND(8, 8) HMY_DECL_BIND(8, 16)
 #define HMY_DECL_BIND_MMA(N_, W_) extern "C" void hmy_bind_mma_##N_##_##W_(const void** fns);
 HMY_DECL_BIND_MMA(4, 1) HMY_DECL_BIND_MMA(8, 1) HMY_DECL_BIND_MMA(14, 1) HMY_DECL_BIND_MMA(16, 1)
 HMY_DECL_BIND_MMA(8, 2) HMY_DECL_BIND_MMA(14, 2) HMY_DECL_BIND_MMA(16, 2)
+
+extern "C" void hmy_bind_tc5_4(const void** fns);
+extern "C" void hmy_bind_tc5_7(const void** fns);
+extern "C" void hmy_bind_tc5_8(const void** fns);
 
 // tensor-core round kernels: d <= 64 and K <= 256 (everything else stays on the SIMT kernels)
 static bool bind_mma(hmy_ctx* ctx) {
@@ -284,6 +293,24 @@ static int plan_round(hmy_ctx* ctx) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, ctx->round_threads, ctx->smem_round));
     if (nb < 1) FAIL("round kernel does not fit on an SM");
     ctx->G = nb * ctx->sms;
+    ctx->use_tc5 = false;
+    if (ctx->want_tc5) {
+        // fail loudly: the option asks for this kernel, there is no silent fallback to another one
+        if (!ctx->use_mma || st.K > 128 || st.d > 64 || st.B > TC5_NB || nblk > 32)
+            FAIL("option tc5: the tensor-memory round kernel needs K <= 128, d <= 64, B <= 32 and at most 32 blocks");
+        const void* f[2] = {nullptr, nullptr};
+        if (st.K <= 64) { hmy_bind_tc5_4(f); ctx->tc5_nc = 4; } else if (st.K <= 112) { hmy_bind_tc5_7(f); ctx->tc5_nc = 7; } else { hmy_bind_tc5_8(f); ctx->tc5_nc = 8; }
+        ctx->fn_tc5 = f[0]; ctx->fn_tc5_fused = f[1];
+        ctx->smem_tc5 = tc5_smem_plan(st.B, ctx->tc5_nc).total;
+        if (ctx->smem_tc5 > 226 * 1024) FAIL("option tc5: round kernel needs more than 226 KB of shared memory");
+        CK(cudaFuncSetAttribute(ctx->fn_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
+        CK(cudaFuncSetAttribute(ctx->fn_tc5_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
+        int nt5 = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt5, ctx->fn_tc5, TC5_TILE, ctx->smem_tc5));
+        if (nt5 < 1) FAIL("option tc5: round kernel does not fit on an SM");
+        ctx->G_tc5 = ctx->sms;            // one CTA per SM: each holds 256 of the SM's 512 tensor-memory columns
+        ctx->use_tc5 = true;
+    }
     // per-round zero block: Told | Dnew | Yacc is separate (ridge also uses it) | obj
     const size_t nT = (size_t)nblk * st.B * st.K;
     ctx->zero_round_bytes = 2 * nT * sizeof(float) + (4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double);
@@ -508,6 +535,14 @@ static int staged_round(hmy_ctx* ctx, int what, int blk) {
     return launch(ctx, ctx->fn_stage, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, false);
 }
 
+// the persistent round kernel (cooperative launch): tensor-memory version when option "tc5" selected it
+static int launch_persistent(hmy_ctx* ctx, void** args) {
+    const bool fk = ctx->fused || ctx->force_fused_kernel;
+    if (ctx->use_tc5)
+        return launch(ctx, fk ? ctx->fn_tc5_fused : ctx->fn_tc5, dim3(ctx->G_tc5), dim3(TC5_TILE), args, ctx->smem_tc5, true);
+    return launch(ctx, fk ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true);
+}
+
 // ---- a2: init ------------------------------------------------------------------------------
 extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj[3]) {
     HmyDev& st = ctx->st;
@@ -530,7 +565,7 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
         if (ctx->fused) ctx->xseq += 1;
         HmyDev s = st; int mode = 1; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, (ctx->fused || ctx->force_fused_kernel) ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
+        if (launch_persistent(ctx, args)) return 1;
         ctx->gen += 1;
     } else {
         if (staged_round(ctx, 2, 0)) return 1;
@@ -577,7 +612,7 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
         if (ctx->fused) ctx->xseq += st.xrelaxed ? 1u : (unsigned int)st.nblk + 1u;
         HmyDev s = st; int mode = 0; unsigned int gen = ctx->gen;
         void* args[] = {&s, &mode, &gen};
-        if (launch(ctx, (ctx->fused || ctx->force_fused_kernel) ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true)) return 1;
+        if (launch_persistent(ctx, args)) return 1;
         ctx->gen += (unsigned int)st.nblk + 1u;
     } else {
         const int64_t nT = (int64_t)st.nblk * st.B * st.K, BK = (int64_t)st.B * st.K;
@@ -727,7 +762,7 @@ extern "C" int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes) {
             return 0;
         }
         case 9: {   // HMY_TRACE: uint64 [grid][HMY_TRACE_SLOTS] globaltimer stamps of the last round
-            const size_t n = (size_t)(ctx->G + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long);
+            const size_t n = (size_t)((ctx->use_tc5 ? ctx->G_tc5 : ctx->G) + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long);
             if (!st.trace) FAIL("hmy_get(trace): tracing is off");
             if ((size_t)bytes != n) FAIL("hmy_get(trace): wrong buffer size");
             CK(cudaStreamSynchronize(ctx->stream));
@@ -764,8 +799,9 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
         CK(cudaSetDevice(ctx->device));
         if (value && !ctx->st.trace) {
             if (!ctx->have_params) FAIL("trace: set params first");
-            if (dev_alloc(ctx, &ctx->st.trace, (size_t)(ctx->G + 1) * HMY_TRACE_SLOTS)) return 1;
-            CK(cudaMemset(ctx->st.trace, 0, (size_t)(ctx->G + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long)));
+            const size_t slots = (size_t)(std::max(ctx->G, ctx->G_tc5) + 1) * HMY_TRACE_SLOTS;
+            if (dev_alloc(ctx, &ctx->st.trace, slots)) return 1;
+            CK(cudaMemset(ctx->st.trace, 0, slots * sizeof(unsigned long long)));
         }
         return 0;
     }
@@ -787,6 +823,10 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
         if (ctx->have_params) FAIL("option mma must be set before hmy_set_params");
         ctx->want_mma = value != 0; return 0;
     }
+    if (n == "tc5") {
+        if (ctx->have_params) FAIL("option tc5 must be set before hmy_set_params");
+        ctx->want_tc5 = value != 0; return 0;
+    }
     if (n == "reset") {
         // back to the freshly-uploaded state (benchmark steps restart from here)
         CK(cudaSetDevice(ctx->device));
@@ -806,14 +846,15 @@ extern "C" int64_t hmy_counter(const hmy_ctx* ctx, const char* name) {
     if (n == "launches") return ctx->launches;
     if (n == "rounds") return ctx->rounds;
     if (n == "ridge_passes") return ctx->ridge_passes;
-    if (n == "grid") return ctx->G;
+    if (n == "grid") return ctx->use_tc5 ? ctx->G_tc5 : ctx->G;
     if (n == "fused") return ctx->fused ? 1 : 0;
-    if (n == "smem_round") return ctx->smem_round;
+    if (n == "smem_round") return ctx->use_tc5 ? ctx->smem_tc5 : ctx->smem_round;
     if (n == "nblk") return ctx->st.nblk;
     if (n == "ncombo") return ctx->st.ncombo;
     if (n == "mma") return ctx->use_mma ? 1 : 0;
     if (n == "ridge_mma") return ctx->ridge_mma ? 1 : 0;
-    if (n == "round_threads") return ctx->round_threads;
+    if (n == "round_threads") return ctx->use_tc5 ? TC5_TILE : ctx->round_threads;
+    if (n == "tc5") return ctx->use_tc5 ? 1 : 0;
     return -1;
 }
 

@@ -96,6 +96,9 @@ int hmy_synchronize(hmy_ctx* ctx);
  *   "mma"        0/1   tensor-core round kernels (default, d <= 64) vs fp32 SIMT; before hmy_set_params
  *   "ridge_mma"  0/1   tensor-core ridge passes (default, d <= 63) vs fp32 SIMT; before hmy_set_params
  *   "mma_wn"     0/2   force two warps along the cluster axis (A/B runs); before hmy_set_params
+ *   "tc5"        0/1   tcgen05 / tensor-memory round kernel for the persistent mode (K <= 128, d <= 64,
+ *                      B <= 32, <= 32 blocks; other shapes FAIL); default 0 until validated on hardware;
+ *                      before hmy_set_params
  *   "relaxed"    0/1   fused multi-GPU mode: exchange the K x B table once per round instead of once
  *                      per block (NOT exact; default 0)
  *   "timing"     0/1   CUDA-event timers around the stages (default 1)
@@ -105,7 +108,7 @@ int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value);
 
 /* Counters: "launches" (kernels launched by this library since creation), "rounds",
  * "ridge_passes", "grid", "nblk", "ncombo", "mma", "ridge_mma", "fused", "round_threads",
- * "smem_round".  Timers (CUDA events on the context stream, milliseconds, cumulative):
+ * "smem_round", "tc5".  Timers (CUDA events on the context stream, milliseconds, cumulative):
  * "ms_round", "ms_ridge", "ms_init".  Unknown names return -1. */
 int64_t hmy_counter(const hmy_ctx* ctx, const char* name);
 double hmy_timer_ms(hmy_ctx* ctx, const char* name);
