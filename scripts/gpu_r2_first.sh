@@ -1,0 +1,20 @@
+#!/bin/bash
+# First GPU call of round 2: hardware verdict on the tcgen05 work written blind at the end of round 1.
+# Everything runs under `timeout` (a hung cooperative kernel must not cost a strike); outputs -> gpurun_out/.
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- bash scripts/gpu_r2_first.sh
+mkdir -p gpurun_out
+A="-gencode arch=compute_100a,code=sm_100a -O2"
+for p in tcgen05_score_probe tcgen05_transposed_probe tcgen05_tile_step_probe; do
+  nvcc $A -o /tmp/$p experiments/$p.cu > gpurun_out/$p.build.log 2>&1 && timeout 60 /tmp/$p > gpurun_out/$p.log 2>&1
+  echo "$p exit $?"; tail -4 gpurun_out/$p.log
+done
+# the product path must still be green before anything else is looked at
+timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -2
+# stage-by-stage numbers first (tells WHERE it is wrong), then the opt-in parity tests
+timeout 300 python tests/tools/debug_tc5.py > gpurun_out/debug_tc5.log 2>&1; echo "debug_tc5 exit $?"; tail -30 gpurun_out/debug_tc5.log
+HMY_TEST_TC5=1 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -k tc5 -x -q -s > gpurun_out/pytest_tc5.log 2>&1; echo "pytest tc5 exit $?"
+grep -E "^\[|passed|failed|Error|error|assert" gpurun_out/pytest_tc5.log | tail -20
+for o in "tc5=0" "tc5=1"; do
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --engine-opt $o > gpurun_out/bench_$o.json 2> gpurun_out/bench_$o.err; echo "bench $o exit $?"
+  python -c "import json; d=json.loads(open('gpurun_out/bench_$o.json').read().strip().splitlines()[-1]); print('$o value', d['value'], 'round ms', d['roofline']['avg_launch_ms'], 'frac', d['roofline']['frac'], 'parity', d.get('parity'))"
+done
