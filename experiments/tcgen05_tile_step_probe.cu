@@ -25,7 +25,9 @@
 //   ./probe_s --selfcheck            # CPU
 //   timeout 60 ./probe_s             # B200
 //
-// Compile-checked and self-checked in the build container; NOT yet run on hardware.
+// Run on a B200 at the very end of round 1 (profiles/r1_tcgen05_probes_b200.txt):
+//   documented convention: R max|err| = 8.056e-07, Yacc rel = 2.220e-06, Oacc rel = 3.466e-06 -> PASS
+//   LBO/SBO exchanged:     R ok (scoring is K-major), Yacc / Oacc wrong                     -> as expected
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <cmath>

@@ -1,9 +1,10 @@
 // tcgen05 / tensor-memory version of the k-means round (opt-in: engine option "tc5").
 //
-// STATUS: written at the end of round 1 after the GPU budget was used up.  The building blocks were
-// probed in experiments/ (tcgen05_score_probe.cu ran on a B200; the transposed operands and the
-// complete tile step of tcgen05_tile_step_probe.cu are compile- and layout-checked only), so this
-// kernel is NOT selected by default and the parity tests only run it when HMY_TEST_TC5=1.
+// STATUS: written at the end of round 1 after the GPU budget was used up.  Its inner loop -- the tile step
+// (1)-(3) below with exactly these layouts, descriptors and fences -- ran stand-alone on a B200
+// (experiments/tcgen05_tile_step_probe.cu: R 8e-7, sums 2-3e-6 against fp64), but THIS kernel, with the
+// block lists, tables and barriers around it, has not run yet: it is NOT selected by default and the parity
+// tests only run it when HMY_TEST_TC5=1.
 //
 // Same algorithm and the same grid-level structure as k_round_mma (hmy_round_mma.cuh): phase 0, the
 // per-CTA K x B tables, the block lists, the barriers and the multi-GPU communication CTA are reused
@@ -111,11 +112,21 @@ __device__ __forceinline__ void tc5_mma(unsigned int tmem, unsigned long long da
 __device__ __forceinline__ void tc5_commit(unsigned long long* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// An MMA that never completes (bad descriptor, lost commit) must become an error, not a hung cooperative
+// grid: after ~2 s of waiting the kernel traps and the host sees a launch failure.
 __device__ __forceinline__ void tc5_wait(unsigned long long* bar, unsigned int parity) {
-    unsigned int done = 0;
-    while (!done)
+    unsigned int done = 0, spins = 0;
+    unsigned long long t0 = 0;
+    while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && (++spins & 1023u) == 0u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) __trap();
+        }
+    }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 __device__ __forceinline__ void tc5_ld16(unsigned int taddr, float (&v)[16]) {
