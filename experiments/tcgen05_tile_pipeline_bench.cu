@@ -1,4 +1,4 @@
-// EXPERIMENT (not product code): throughput of the tensor-memory tile step of the clustering round under three
+// EXPERIMENT (not product code): throughput of the tensor-memory tile step of the clustering round under four
 // ways of feeding and overlapping it -- the measurement the next version of hmy_round_tc5.cuh is designed from.
 //
 // One persistent CTA per SM walks its share of the cells block by block (20 blocks, cells of a block = a 5 %
@@ -13,6 +13,8 @@
 //   MODE 2  "pipelined" MODE 1 with three Z buffers and two score accumulators: the gather of tile t+2 and the
 //                       scoring of tile t+1 run under the epilogue of tile t; the R row is stored to HBM after
 //                       the accumulation MMAs have been issued
+//   MODE 2 / 256 threads the same with the clusters of a cell split over two warps (warps w and w+4 read the same
+//                       tensor-memory lanes): 56 scores per thread, two warps per scheduler
 //
 // No grid barriers, no phase 0, no penalty-table update: this isolates the tile step (the rest of the round is
 // the same code as today).  Output: microseconds per pass over all cells and per tile, for each mode; all modes
@@ -33,7 +35,6 @@
 #include <vector>
 
 constexpr int TILE = 128, DP = 64, DPF = 52, D = 50, K = 100, KP = 112, KM = 128, NB = 32, NLEV = 8, NBLK = 20;
-constexpr int NC = KP / 16;
 constexpr float OPSCALE = 1024.f, ACCSCALE = 1.f / 1048576.f;
 constexpr int TMEM_COLS = 512;                 // D1[0]: [0,112)  D1[1]: [128,240)  D2y: [256,320)  D2o: [320,352)
 constexpr int COL_D1B = 128, COL_Y = 256, COL_O = 320;
@@ -85,6 +86,16 @@ __device__ inline void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
 }
+__device__ inline void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t u[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(u[j]);
+}
 __device__ inline void publish() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -118,13 +129,17 @@ struct Args {
     float* R;                // [N][KP]
     float* Yslab;            // [G][KM][DP]
     float* Oslab;            // [G][KM][NB]
-    float* obj;              // [G][128][2]
+    float* obj;              // [G][256][2]
 };
 
 // ---- one CTA ------------------------------------------------------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
+template <int MODE, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
     constexpr int NZ = (MODE == 2) ? 3 : 1;          // Z / one-hot buffers
+    constexpr int H = NTHR / 128;                    // threads per cell (each owns CW clusters)
+    constexpr int CW = KP / H;
+    static_assert(H == 1 || (H == 2 && MODE == 2), "256 threads: pipelined mode only");
+    static_assert(CW % 8 == 0, "column split");
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sZ = smem;                              // NZ x (hi | lo)
     unsigned char* sO = sZ + NZ * 2 * SZ;                  // NZ x one-hot
@@ -136,9 +151,11 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
     float* sc1 = sP + NLEV * KP;
     float* sc3 = sc1 + KP;
     int* sCell = reinterpret_cast<int*>(sc3 + KP);         // [128] (MODE 0 gather)
+    float* sXch = reinterpret_cast<float*>(sCell + 128);   // [2][128][2] partial row sums (H = 2)
     __shared__ __align__(8) uint64_t bar_s[2], bar_a;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int ct = tid & 127, half = tid >> 7, cb = half * CW;     // this thread's cell of the tile / first cluster
 
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "n"(TMEM_COLS));
@@ -150,7 +167,7 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar_a)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < KP * (DP / 2); i += 128) {
+    for (int i = tid; i < KP * (DP / 2); i += NTHR) {
         const int k = i / (DP / 2), j = 2 * (i % (DP / 2));
         uint32_t hi, lo;
         split2(a.Y[k * DP + j] * OPSCALE, a.Y[k * DP + j + 1] * OPSCALE, hi, lo);
@@ -158,17 +175,17 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
         *reinterpret_cast<uint32_t*>(sYh + off) = hi;
         *reinterpret_cast<uint32_t*>(sYl + off) = lo;
     }
-    for (int i = tid; i < NLEV * KP; i += 128) sP[i] = a.P[i];
-    for (int k = tid; k < KP; k += 128) {
+    for (int i = tid; i < NLEV * KP; i += NTHR) sP[i] = a.P[i];
+    for (int k = tid; k < KP; k += NTHR) {
         const float sg = a.sigma[k];
         sc1[k] = (k < K) ? (2.0f * 1.4426950408889634f / sg) * ACCSCALE : 0.f;
         sc3[k] = (k < K) ? sg * 0.6931471805599453f : 0.f;
     }
-    for (int i = tid; i < (NZ * (2 * SZ + SO) + 2 * SR) / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < (NZ * (2 * SZ + SO) + 2 * SR) / 16; i += NTHR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tbase = tmem_base, lane_base = (uint32_t)(32 * warp) << 16;
+    const uint32_t tbase = tmem_base, lane_base = (uint32_t)(32 * (warp & 3)) << 16;
     const uint32_t sb = smem_u32(smem);
     const uint32_t id_score = make_idesc(TILE, KP, 0, 0), id_y = make_idesc(KM, DP, 1, 1), id_o = make_idesc(KM, NB, 1, 1);
 
@@ -185,7 +202,7 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
         unsigned char* Zh = sZ + b * 2 * SZ;
         unsigned char* Zl = Zh + SZ;
         // one-hot level row of this thread's cell
-        {
+        if (tid < 128) {
             const int lv = (tid < nt) ? a.lev[a.list[off + tid]] : -1;
 #pragma unroll
             for (int j = 0; j < NB / 8; ++j) {
@@ -227,8 +244,8 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
         } else {
             // 16 chunks of 16 B per row: chunks 0..7 = hi PCs 8c..8c+7, 8..15 = lo; 16 consecutive threads = one row
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-                const int q = tid + u * 128, row = q >> 4, ch = q & 15;
+            for (int u = 0; u < 2048 / NTHR; ++u) {
+                const int q = tid + u * NTHR, row = q >> 4, ch = q & 15;
                 if (row < nt) {
                     const int cell = a.list[off + row];
                     const uint32_t dst = smem_u32((ch < 8 ? Zh : Zl) + (row >> 3) * Z_SBO_K + (ch & 7) * Z_LBO_K + (row & 7) * 16);
@@ -272,46 +289,59 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
     };
     // thread = cluster: level sums of the finished block -> this CTA's slab
     auto flush_block = [&]() {
-        float v0[16], v1[16];
-        tmem_ld16(tbase + lane_base + COL_O, v0);
-        tmem_ld16(tbase + lane_base + COL_O + 16, v1);
+        if (tid < 128) {                              // whole warps: tcgen05.ld is warp-collective
+            float v0[16], v1[16];
+            tmem_ld16(tbase + lane_base + COL_O, v0);
+            tmem_ld16(tbase + lane_base + COL_O + 16, v1);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { Oslab[tid * NB + j] += v0[j] * (1.f / OPSCALE); Oslab[tid * NB + 16 + j] += v1[j] * (1.f / OPSCALE); }
+            for (int j = 0; j < 16; ++j) { Oslab[tid * NB + j] += v0[j] * (1.f / OPSCALE); Oslab[tid * NB + 16 + j] += v1[j] * (1.f / OPSCALE); }
+        }
         o_started = false;
     };
     // epilogue of one tile, thread = cell.  E stays in registers; store_global = false defers the HBM row
-    float E[KP];
+    float E[CW];
     float sc = 0.f;
-    auto epilogue = [&](int d1, int cell, int lv, bool valid) {
+    auto epilogue = [&](int d1, int lv, bool valid) {
         float ss = 0.f, sp = 0.f, sd = 0.f;
         const float* Pr = sP + (valid ? lv : 0) * KP;
+        auto cols4 = [&](const float* acc, int col, int e0) {      // 4 clusters starting at `col` (a multiple of 4)
+            const float4 k1 = *reinterpret_cast<const float4*>(sc1 + col), k3 = *reinterpret_cast<const float4*>(sc3 + col), pn = *reinterpret_cast<const float4*>(Pr + col);
+            const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k3v[4] = {k3.x, k3.y, k3.z, k3.w}, pv[4] = {pn.x, pn.y, pn.z, pn.w};
 #pragma unroll
-        for (int ch = 0; ch < NC; ++ch) {
-            float acc[16];
-            tmem_ld16(tbase + lane_base + (uint32_t)(d1 * COL_D1B + 16 * ch), acc);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int col = 16 * ch + 4 * q;
-                const float4 k1 = *reinterpret_cast<const float4*>(sc1 + col), k3 = *reinterpret_cast<const float4*>(sc3 + col), pn = *reinterpret_cast<const float4*>(Pr + col);
-                const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k3v[4] = {k3.x, k3.y, k3.z, k3.w}, pv[4] = {pn.x, pn.y, pn.z, pn.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float t = fmaf(-acc[4 * q + e], k1v[e], k1v[e] * 1048576.0f);
-                    const float s = (col + e < K) ? ex2_approx(-t) : 0.f;
-                    ss += s;
-                    const float ev = s * pv[e];
-                    sp += ev;
-                    sd = fmaf(k3v[e], ev * t, sd);
-                    E[col + e] = ev;
-                }
+            for (int e = 0; e < 4; ++e) {
+                const float t = fmaf(-acc[e], k1v[e], k1v[e] * 1048576.0f);
+                const float s = (col + e < K) ? ex2_approx(-t) : 0.f;
+                ss += s;
+                const float ev = s * pv[e];
+                sp += ev;
+                sd = fmaf(k3v[e], ev * t, sd);
+                E[e0 + e] = ev;
             }
+        };
+#pragma unroll
+        for (int ch = 0; ch < CW / 16; ++ch) {
+            float acc[16];
+            tmem_ld16(tbase + lane_base + (uint32_t)(d1 * COL_D1B + cb + 16 * ch), acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cols4(acc + 4 * q, cb + 16 * ch + 4 * q, 16 * ch + 4 * q);
+        }
+        if (CW % 16 == 8) {
+            float acc[8];
+            tmem_ld8(tbase + lane_base + (uint32_t)(d1 * COL_D1B + cb + CW - 8), acc);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) cols4(acc + 4 * q, cb + CW - 8 + 4 * q, CW - 8 + 4 * q);
+        }
+        if (H == 2) {                                  // the two halves of a cell exchange their row sums
+            sXch[(half * 128 + ct) * 2] = ss; sXch[(half * 128 + ct) * 2 + 1] = sp;
+            __syncthreads();
+            ss += sXch[((half ^ 1) * 128 + ct) * 2]; sp += sXch[((half ^ 1) * 128 + ct) * 2 + 1];
         }
         const float is = 1.f / ss;
         sc = valid ? is / fmaxf(sp * is, 1e-8f) : 0.f;
         float oe = 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < KP; c0 += 8) {
-            const float4 k3a = *reinterpret_cast<const float4*>(sc3 + c0), k3b = *reinterpret_cast<const float4*>(sc3 + c0 + 4);
+        for (int c0 = 0; c0 < CW; c0 += 8) {
+            const float4 k3a = *reinterpret_cast<const float4*>(sc3 + cb + c0), k3b = *reinterpret_cast<const float4*>(sc3 + cb + c0 + 4);
             const float k3v[8] = {k3a.x, k3a.y, k3a.z, k3a.w, k3b.x, k3b.y, k3b.z, k3b.w};
             float r[8];
 #pragma unroll
@@ -324,18 +354,17 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
             split2(r[2] * OPSCALE, r[3] * OPSCALE, hi.y, lo.y);
             split2(r[4] * OPSCALE, r[5] * OPSCALE, hi.z, lo.z);
             split2(r[6] * OPSCALE, r[7] * OPSCALE, hi.w, lo.w);
-            const int off = (c0 >> 3) * R_SBO + (tid >> 3) * R_LBO + (tid & 7) * 16;
+            const int off = ((cb + c0) >> 3) * R_SBO + (ct >> 3) * R_LBO + (ct & 7) * 16;
             *reinterpret_cast<uint4*>(sRh + off) = hi;
             *reinterpret_cast<uint4*>(sRl + off) = lo;
         }
         if (valid) { objd += sc * sd; obje += oe; }
-        (void)cell;
     };
     auto store_row = [&](int cell, bool valid) {
         if (!valid) return;
-        float* Rg = a.R + (size_t)cell * KP;
+        float* Rg = a.R + (size_t)cell * KP + cb;
 #pragma unroll
-        for (int c0 = 0; c0 < KP; c0 += 4)
+        for (int c0 = 0; c0 < CW; c0 += 4)
             *reinterpret_cast<float4*>(Rg + c0) = make_float4(E[c0] * sc, E[c0 + 1] * sc, E[c0 + 2] * sc, E[c0 + 3] * sc);
     };
 
@@ -350,10 +379,10 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
             if (MODE == 1) cp_async_wait<0>();
             publish();
             issue_score(0, 0);
-            const bool valid = tid < nt;
-            const int cell = valid ? a.list[off + tid] : 0, lv = valid ? a.lev[cell] : 0;
+            const bool valid = ct < nt;
+            const int cell = valid ? a.list[off + ct] : 0, lv = valid ? a.lev[cell] : 0;
             wait_parity(&bar_s[0], ph_s & 1u); ph_s++;
-            epilogue(0, cell, lv, valid);
+            epilogue(0, lv, valid);
             store_row(cell, valid);
             publish();
             issue_acc(0, nt);
@@ -380,17 +409,17 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
                 if (a.tile_nt[t_begin + t - 1] >> 30) flush_block();
             }
             if (t + 2 < T) load_tile(t + 2, (t + 2) % 3);          // = buffer of tile t-1
-            const bool valid = tid < nt;
-            const int cell = valid ? a.list[off + tid] : 0, lv = valid ? a.lev[cell] : 0;
+            const bool valid = ct < nt;
+            const int cell = valid ? a.list[off + ct] : 0, lv = valid ? a.lev[cell] : 0;
             wait_parity(&bar_s[t & 1], (uint32_t)(t >> 1) & 1u);
-            epilogue(t & 1, cell, lv, valid);
+            epilogue(t & 1, lv, valid);
             publish();
             issue_acc(t % 3, nt);
             store_row(cell, valid);                  // HBM stores overlap the accumulation MMAs
         }
     }
     if (T > 0) { wait_parity(&bar_a, ph_a & 1u); ph_a++; flush_block(); }
-    if (y_started) {
+    if (y_started && tid < 128) {
 #pragma unroll
         for (int ch = 0; ch < DP / 16; ++ch) {
             float v[16];
@@ -399,8 +428,8 @@ __global__ void __launch_bounds__(128, 1) tile_pipeline(Args a) {
             for (int j = 0; j < 16; ++j) Yslab[tid * DP + 16 * ch + j] = v[j] * ACCSCALE;
         }
     }
-    a.obj[((size_t)blockIdx.x * 128 + tid) * 2] = objd;
-    a.obj[((size_t)blockIdx.x * 128 + tid) * 2 + 1] = obje;
+    a.obj[((size_t)blockIdx.x * 256 + tid) * 2] = objd;
+    a.obj[((size_t)blockIdx.x * 256 + tid) * 2 + 1] = obje;
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "n"(TMEM_COLS));
@@ -466,7 +495,7 @@ static Dev to_device(const Host& h) {
     Dev d{}; d.G = h.G; d.N = h.N;
     d.a.Zf = upload(h.Zf); d.a.Zs = upload(h.Zs); d.a.Y = upload(h.Y); d.a.sigma = upload(h.sigma); d.a.P = upload(h.P);
     d.a.lev = upload(h.lev); d.a.list = upload(h.list); d.a.tile_first = upload(h.tile_first); d.a.tile_off = upload(h.tile_off); d.a.tile_nt = upload(h.tile_nt);
-    CK(cudaMalloc(&d.R, (size_t)h.N * KP * 4)); CK(cudaMalloc(&d.Ys, (size_t)h.G * KM * DP * 4)); CK(cudaMalloc(&d.Os, (size_t)h.G * KM * NB * 4)); CK(cudaMalloc(&d.obj, (size_t)h.G * 128 * 2 * 4));
+    CK(cudaMalloc(&d.R, (size_t)h.N * KP * 4)); CK(cudaMalloc(&d.Ys, (size_t)h.G * KM * DP * 4)); CK(cudaMalloc(&d.Os, (size_t)h.G * KM * NB * 4)); CK(cudaMalloc(&d.obj, (size_t)h.G * 256 * 2 * 4));
     d.a.R = d.R; d.a.Yslab = d.Ys; d.a.Oslab = d.Os; d.a.obj = d.obj;
     return d;
 }
@@ -478,20 +507,23 @@ static void free_device(Dev& d) {
 
 static size_t smem_bytes(int mode) {
     const int NZ = mode == 2 ? 3 : 1;
-    return (size_t)NZ * (2 * SZ + SO) + 2 * SR + 2 * SY + (NLEV * KP + 2 * KP) * 4 + 128 * 4 + 1024;
+    return (size_t)NZ * (2 * SZ + SO) + 2 * SR + 2 * SY + (NLEV * KP + 2 * KP) * 4 + 128 * 4 + 2 * 128 * 2 * 4 + 1024;
 }
-template <int MODE> static void launch(Dev& d) {
+template <int MODE, int NTHR> static void launch(Dev& d) {
     static bool attr = false;
-    if (!attr) { CK(cudaFuncSetAttribute(tile_pipeline<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MODE))); attr = true; }
-    CK(cudaMemset(d.Ys, 0, (size_t)d.G * KM * DP * 4)); CK(cudaMemset(d.Os, 0, (size_t)d.G * KM * NB * 4));
-    tile_pipeline<MODE><<<d.G, 128, smem_bytes(MODE)>>>(d.a);
+    if (!attr) { CK(cudaFuncSetAttribute(tile_pipeline<MODE, NTHR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(MODE))); attr = true; }
+    tile_pipeline<MODE, NTHR><<<d.G, NTHR, smem_bytes(MODE)>>>(d.a);
 }
-static void launch_mode(int mode, Dev& d) { if (mode == 0) launch<0>(d); else if (mode == 1) launch<1>(d); else launch<2>(d); }
+// variant 0..3: the three modes with 128 threads, then the pipelined mode with 256
+static void launch_variant(int v, Dev& d) {
+    if (v == 0) launch<0, 128>(d); else if (v == 1) launch<1, 128>(d); else if (v == 2) launch<2, 128>(d); else launch<2, 256>(d);
+}
+static void zero_slabs(Dev& d) { CK(cudaMemset(d.Ys, 0, (size_t)d.G * KM * DP * 4)); CK(cudaMemset(d.Os, 0, (size_t)d.G * KM * NB * 4)); }
 
 int main(int argc, char** argv) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int G = prop.multiProcessorCount;
-    const char* names[3] = {"v1 (fp32 gather, synchronous)", "presplit cp.async, synchronous", "presplit cp.async, pipelined"};
+    const char* names[4] = {"v1 (fp32 gather, synchronous)", "presplit cp.async, synchronous", "presplit cp.async, pipelined", "pipelined, 256 threads"};
     int bad = 0;
     {   // ---- correctness at a small N (every tile ragged) and at a medium N against fp64
         const int N = (argc > 1) ? atoi(argv[1]) : 131072;
@@ -513,9 +545,10 @@ int main(int argc, char** argv) {
             }
         }
         Dev d = to_device(h);
-        for (int mode = 0; mode < 3; ++mode) {
+        for (int mode = 0; mode < 4; ++mode) {
             CK(cudaMemset(d.R, 0xff, (size_t)N * KP * 4));
-            launch_mode(mode, d);
+            zero_slabs(d);
+            launch_variant(mode, d);
             cudaError_t e = cudaDeviceSynchronize();
             if (e != cudaSuccess) { printf("mode %d: CUDA error %s\nFAIL\n", mode, cudaGetErrorString(e)); return 1; }
             std::vector<float> R((size_t)N * KP), Ys((size_t)G * KM * DP), Os((size_t)G * KM * NB);
@@ -537,13 +570,13 @@ int main(int argc, char** argv) {
         Dev d = to_device(h);
         const int tiles = (int)h.tile_off.size();
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-        for (int mode = 0; mode < 3; ++mode) {
-            launch_mode(mode, d); CK(cudaDeviceSynchronize());
+        for (int mode = 0; mode < 4; ++mode) {
+            zero_slabs(d); launch_variant(mode, d); CK(cudaDeviceSynchronize());
             float best = 1e30f, sum = 0;
             for (int it = 0; it < 5; ++it) {
-                CK(cudaMemset(d.Ys, 0, (size_t)G * KM * DP * 4)); CK(cudaMemset(d.Os, 0, (size_t)G * KM * NB * 4));
+                zero_slabs(d);
                 CK(cudaEventRecord(e0));
-                if (mode == 0) tile_pipeline<0><<<G, 128, smem_bytes(0)>>>(d.a); else if (mode == 1) tile_pipeline<1><<<G, 128, smem_bytes(1)>>>(d.a); else tile_pipeline<2><<<G, 128, smem_bytes(2)>>>(d.a);
+                launch_variant(mode, d);
                 CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = fminf(best, ms); sum += ms;
             }
