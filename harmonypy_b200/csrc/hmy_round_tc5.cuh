@@ -218,9 +218,12 @@ __device__ void tc5_load_round_constants(Tc5Ctx<NC>& c, const HmyDev& st, float*
 // Stage one tile -- ids / levels of its cells (registers: thread = cell), the one-hot level rows, the Z_cos
 // rows as fp16 hi/lo -- and issue its scoring.  Independent of the penalty table, so the first tile of the
 // NEXT block is staged and scored before the grid barrier is waited on.
+// trb: first of 5 timeline slots of this tile (>= HMY_TRACE_SLOTS: none): stage begin, operands published,
+// scores ready, epilogue done, R tile published.
 template <int NC>
-__device__ void tc5_stage_tile(Tc5Ctx<NC>& c, const HmyDev& st, const int* list, long long tb, int nt) {
+__device__ void tc5_stage_tile(Tc5Ctx<NC>& c, const HmyDev& st, const int* list, long long tb, int nt, int trb) {
     const int tid = threadIdx.x;
+    hmy_trace(st, trb);
     tc5_wait_acc(c);
     c.valid = tid < nt;
     int cell = 0, combo = 0;
@@ -275,6 +278,7 @@ __device__ void tc5_stage_tile(Tc5Ctx<NC>& c, const HmyDev& st, const int* list,
         }
     }
     tc5_publish();
+    hmy_trace(st, trb + 1);
     if (tid == 0) {
         const unsigned int sb = smem_u32(c.base), id_score = tc5_idesc(TC5_TILE, 16 * NC, 0, 0);
         const unsigned long long dZh = tc5_desc(sb + TC5_OFF_ZH, TC5_Z_LBO_K, TC5_Z_SBO_K), dZl = tc5_desc(sb + TC5_OFF_ZL, TC5_Z_LBO_K, TC5_Z_SBO_K);
@@ -291,11 +295,12 @@ __device__ void tc5_stage_tile(Tc5Ctx<NC>& c, const HmyDev& st, const int* list,
 
 // Epilogue of the staged tile (thread = cell) and its contribution to the sums.
 template <int NC>
-__device__ void tc5_finish_tile(Tc5Ctx<NC>& c, const HmyDev& st, bool init, int nt) {
+__device__ void tc5_finish_tile(Tc5Ctx<NC>& c, const HmyDev& st, bool init, int nt, int trb) {
     constexpr int KT2 = 16 * NC;
     const int tid = threadIdx.x, K = st.K, Kp = st.Kp, V = st.V;
     tc5_wait(&c.bar[0], c.ph_score & 1u);
     c.ph_score++;
+    hmy_trace(st, trb + 2);
     float E[KT2];
     float ss = 0.f, sp = 0.f, sd = 0.f;
     // ---- S = exp(-dist/sigma) (harmony.py:466-467), times the penalty (harmony.py:500)
@@ -361,7 +366,9 @@ __device__ void tc5_finish_tile(Tc5Ctx<NC>& c, const HmyDev& st, bool init, int 
         *reinterpret_cast<uint4*>(c.Rl() + off) = lo;
     }
     if (c.valid) { c.objd += (double)(sc * sd); c.obje += (double)oe; }
+    hmy_trace(st, trb + 3);
     tc5_publish();
+    hmy_trace(st, trb + 4);
     // ---- sums over the cells of the tile (K-dim = cells, 16 per step)
     if (tid == 0) {
         const unsigned int sb = smem_u32(c.base), id_y = tc5_idesc(TC5_KM, TC5_DP, 1, 1), id_o = tc5_idesc(TC5_KM, TC5_NB, 1, 1);
@@ -414,10 +421,12 @@ __device__ void tc5_flush_block(Tc5Ctx<NC>& c, const HmyDev& st, int blk) {
 template <int NC>
 __device__ void tc5_process_block(Tc5Ctx<NC>& c, const HmyDev& st, int blk, const int* list,
                                   long long lbeg, long long lend, bool init, long long staged_tb) {
+    int trb = (blk == 5 && !init) ? 64 : HMY_TRACE_SLOTS;          // per-tile timeline of block 5 (option "trace")
     for (long long tb = lbeg; tb < lend; tb += TC5_TILE) {
         const int nt = (int)min((long long)TC5_TILE, lend - tb);
-        if (tb != staged_tb) tc5_stage_tile(c, st, list, tb, nt);
-        tc5_finish_tile(c, st, init, nt);
+        if (tb != staged_tb) tc5_stage_tile(c, st, list, tb, nt, trb);
+        tc5_finish_tile(c, st, init, nt, trb);
+        if (trb < HMY_TRACE_SLOTS - 10) trb += 5; else trb = HMY_TRACE_SLOTS;
     }
     tc5_flush_block(c, st, blk);
 }
@@ -519,7 +528,7 @@ __global__ void __launch_bounds__(TC5_TILE, 1) k_round_tc5(HmyDev st, int mode, 
         {
             long long nb, ne;
             block_share(st, 0, blockIdx.x, G, nb, ne);
-            if (nb < ne) { tc5_stage_tile(c, st, st.list, nb, (int)min((long long)TC5_TILE, ne - nb)); staged = nb; }
+            if (nb < ne) { tc5_stage_tile(c, st, st.list, nb, (int)min((long long)TC5_TILE, ne - nb), HMY_TRACE_SLOTS); staged = nb; }
         }
         const bool multi = multi_any && !st.xrelaxed;      // exact mode: one table exchange per block
         if (multi_any) worker_barrier(st, gen++);          // comm CTA: all Told sums are in (+ exchange)
@@ -536,7 +545,7 @@ __global__ void __launch_bounds__(TC5_TILE, 1) k_round_tc5(HmyDev st, int mode, 
             if (blk + 1 < st.nblk) {        // next block's first tile: stage and score before waiting at the barrier
                 long long nb, ne;
                 block_share(st, blk + 1, blockIdx.x, G, nb, ne);
-                if (nb < ne) { tc5_stage_tile(c, st, st.list, nb, (int)min((long long)TC5_TILE, ne - nb)); staged = nb; }
+                if (nb < ne) { tc5_stage_tile(c, st, st.list, nb, (int)min((long long)TC5_TILE, ne - nb), blk + 1 == 5 ? 64 : HMY_TRACE_SLOTS); staged = nb; }
                 if (multi_any) worker_barrier(st, gen++);
                 else grid_barrier(st, G, gen++);
             } else {

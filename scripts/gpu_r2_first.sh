@@ -21,3 +21,4 @@ for o in "tc5=0" "tc5=1"; do
   timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --engine-opt $o > gpurun_out/bench_$o.json 2> gpurun_out/bench_$o.err; echo "bench $o exit $?"
   python -c "import json; d=json.loads(open('gpurun_out/bench_$o.json').read().strip().splitlines()[-1]); print('$o value', d['value'], 'round ms', d['roofline']['avg_launch_ms'], 'frac', d['roofline']['frac'], 'parity', d.get('parity'))"
 done
+HMY_ENGINE_OPTS=tc5=1 timeout 300 python scripts/trace_round.py syn1m > gpurun_out/trace_tc5.txt 2>&1; echo "trace tc5 exit $?"; tail -24 gpurun_out/trace_tc5.txt

@@ -14,7 +14,9 @@ Z, codes = make_synthetic_arrays(N, w["d"], w["levels"], seed=0)
 Pr_b = bench.global_level_probs(w, N, 0, N, codes)
 Y0 = bench.init_centroids(w, N)
 prob = bench.make_problem(w, Z, codes, Pr_b, N, 0)
-ho = Harmony(prob, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, 0, 0, perm_mode="device", run=False)
+# engine options from the environment, e.g. HMY_ENGINE_OPTS="tc5=1"
+opts = {k: int(v) for k, v in (kv.split("=") for kv in os.environ.get("HMY_ENGINE_OPTS", "").split(",") if kv)}
+ho = Harmony(prob, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, 0, 0, perm_mode="device", run=False, engine_options=opts or None)
 eng = ho._engine
 ho.init_cluster(0, Y0)
 for _ in range(3):
@@ -50,10 +52,15 @@ for name, a, b in (("fence", 0, 1), ("body+sync", 1, 2), ("reset+fence", 2, 3), 
 # per-tile stamps of block 5 (thread 0 = warp 0): tile start, ids ready, Z ready, scores done, epilogue done, sync, Y-GEMM done
 tt = t[:, 64:125]
 names = ["ids+lev load", "Z gather", "score MMA", "epilogue", "sync wait", "Y-GEMM"]
+nst = 7
+if eng.counter("tc5") == 1:
+    # tensor-memory kernel: 5 stamps per tile (stage begin, operands published, scores ready, epilogue done, R published)
+    names = ["(pre-staged) gather+publish", "barrier + tables + score wait", "epilogue", "publish R", "next: stage begin"]
+    nst = 6
 rows = []
 for c in range(G):
     x = tt[c]; x = x[x > 0]
-    if len(x) >= 8: rows.append(x[:7] - x[0])
+    if len(x) >= nst + 1: rows.append(x[:nst] - x[0])
 rows = np.array(rows)
 print("first tile of block 5, cumulative us (mean over CTAs):", np.round(rows.mean(axis=0) / 1e3, 2), names)
 pr5 = t[:, 4 + 15] - t[:, 3 + 15]
