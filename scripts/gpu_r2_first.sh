@@ -11,6 +11,8 @@ done
 # tile-step throughput under three feeding / overlap schemes (design input for the next tc5 version)
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/pipe_bench experiments/tcgen05_tile_pipeline_bench.cu > gpurun_out/pipe_bench.build.log 2>&1 \
   && timeout 180 /tmp/pipe_bench > gpurun_out/pipe_bench.log 2>&1; echo "pipe_bench exit $?"; tail -8 gpurun_out/pipe_bench.log
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -rdc=true -o /tmp/gbar experiments/grid_barrier_bench.cu > gpurun_out/gbar.build.log 2>&1 \
+  && timeout 60 /tmp/gbar > gpurun_out/gbar.log 2>&1; echo "grid barrier bench exit $?"; cat gpurun_out/gbar.log
 # the product path must still be green before anything else is looked at
 timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -2
 # stage-by-stage numbers first (tells WHERE it is wrong), then the opt-in parity tests
