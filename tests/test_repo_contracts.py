@@ -54,3 +54,24 @@ def test_design_and_integration_documents_exist_and_cite_the_reference():
     for name in ("DESIGN.md", "INTEGRATION.md"):
         text = open(os.path.join(ROOT, name)).read()
         assert "harmony.py:" in text and len(text) > 3000
+
+
+def test_every_engine_option_and_counter_is_documented_in_the_header():
+    """include/harmony_b200.h is the contract: each name hmy_set_option / hmy_counter / hmy_timer_ms accepts
+    must appear in its comment block (force_fused_kernel is a codegen A/B switch, deliberately undocumented)."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    api = open(os.path.join(root, "harmonypy_b200", "csrc", "hmy_api.cu")).read()
+    header = open(os.path.join(root, "include", "harmony_b200.h")).read()
+
+    def names_in(func):
+        body = api[api.index(f'extern "C" {func}'):]
+        body = body[:body.index("\n}\n")]
+        return set(re.findall(r'n == "([a-z_0-9]+)"', body))
+
+    opts = names_in("int hmy_set_option") - {"force_fused_kernel"}
+    ctrs = names_in("int64_t hmy_counter")
+    tmrs = names_in("double hmy_timer_ms")
+    assert {"persistent", "mma", "tc5", "trace"} <= opts and {"launches", "grid", "tc5"} <= ctrs and "ms_round" in tmrs
+    missing = sorted(n for n in opts | ctrs | tmrs if f'"{n}"' not in header)
+    assert not missing, f"undocumented in include/harmony_b200.h: {missing}"
