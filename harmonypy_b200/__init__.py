@@ -10,4 +10,7 @@ def __getattr__(name):
     if name in ("run_harmony", "Harmony"):
         from . import harmony
         return getattr(harmony, name)
+    if name == "compute_lisi":
+        from .lisi import compute_lisi
+        return compute_lisi
     raise AttributeError(name)

@@ -39,6 +39,7 @@ SYMBOLS = {
     "hmy_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p]),
     "hmy_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmy_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "hmy_lisi_compute": (C.c_int, [C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_double, C.c_void_p]),
 }
 
 _lib = None

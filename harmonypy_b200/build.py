@@ -69,6 +69,7 @@ def build(force=False, jobs=None, verbose=True):
     for nt, wn in MMA_INSTANCES:
         work.append((os.path.join(CSRC, "hmy_inst_mma.cu"), os.path.join(OBJ, f"hmy_inst_mma_{nt}_{wn}.o"),
                      [f"-DHMY_NT={nt}", f"-DHMY_WN={wn}"]))
+    work.append((os.path.join(CSRC, "hmy_lisi.cu"), os.path.join(OBJ, "hmy_lisi.o"), []))
     for nc in TC5_INSTANCES:
         work.append((os.path.join(CSRC, "hmy_inst_tc5.cu"), os.path.join(OBJ, f"hmy_inst_tc5_{nc}.o"),
                      [f"-DHMY_TC5_NC={nc}"]))

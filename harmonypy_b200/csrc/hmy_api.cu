@@ -161,6 +161,9 @@ static bool bind_for(hmy_ctx* ctx) {
 
 extern "C" const char* hmy_version(void) { return HMY_VERSION; }
 
+// failure channel of the context-free entry points in other translation units (hmy_lisi.cu)
+extern "C" void harmony_b200_set_global_error(const char* msg) { g_create_error = msg ? msg : ""; }
+
 extern "C" const char* hmy_last_error(const hmy_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_global, int64_t cell_offset,

@@ -124,6 +124,17 @@ int hmy_set_allreduce(hmy_ctx* ctx, hmy_allreduce_fn fn, void* user);
 int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B);
 int hmy_comm_attach(hmy_ctx* ctx, int rank, int world, const void* all_handles_world_x_64B);
 
+/* ---- evaluation metric (not on the harmonize() path) ---------------------- */
+
+/* compute_lisi (harmonypy/lisi.py:24-65): exact k = int(3 * perplexity) nearest neighbours of every cell
+ * (Euclidean, fp64, the cell itself dropped afterwards like lisi.py:56-57), per-cell bisection on beta until the
+ * entropy of exp(-beta * dist) equals log(perplexity) (lisi.py:68-122), inverse Simpson index of each label
+ * column under those weights (lisi.py:127-132, :64).
+ * X_host: n x d row-major doubles; codes_host: n_labels x n int32 category codes (pd.Categorical codes);
+ * out_host: n x n_labels doubles.  Context-free; failures are reported through hmy_last_error(NULL). */
+int hmy_lisi_compute(int device, int64_t n, int d, const double* X_host, int n_labels,
+                     const int32_t* codes_host, double perplexity, double* out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,21 @@ def test_create_validates_arguments(lib):
     assert b"K" in lib.hmy_last_error(None)
     assert lib.hmy_create(C.byref(h), 0, 100, 50, 0, 30, 10, 1, p) != 0
     assert b"n_global" in lib.hmy_last_error(None)
+
+
+def test_lisi_entry_point_validates_and_refuses_to_run_without_gpu(lib):
+    import pandas as pd
+    import torch
+    import harmonypy_b200 as hm
+    from harmonypy_b200 import _cabi
+    X = np.random.default_rng(0).normal(size=(50, 4))
+    meta = pd.DataFrame({"a": pd.Categorical(["x", "y"] * 25)})
+    with pytest.raises(_cabi.EngineError, match="fewer cells"):
+        hm.compute_lisi(X, meta, ["a"], 30)                       # 90 neighbours of 50 cells (checked before any CUDA call)
+    X = np.random.default_rng(0).normal(size=(500, 4))
+    meta = pd.DataFrame({"a": pd.Categorical(["x", "y"] * 250)})
+    with pytest.raises(_cabi.EngineError, match="perplexity"):
+        hm.compute_lisi(X, meta, ["a"], 60)                       # 180 > 128 neighbours
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.EngineError, match="hmy_lisi_compute"):
+            hm.compute_lisi(X, meta, ["a"], 30)                   # no CPU fallback
