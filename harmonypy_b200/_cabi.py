@@ -29,6 +29,7 @@ SYMBOLS = {
                                  C.c_double]),
     "hmy_set_data": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmy_init_from_centroids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "hmy_kmeans_init": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_kmeans_round": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_ridge_correct": (C.c_int, [C.c_void_p]),
     "hmy_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
@@ -134,6 +135,14 @@ class Engine:
         obj = (C.c_double * 3)()
         self._ck(self.lib.hmy_init_from_centroids(self.h, _ptr(Y0), obj), "hmy_init_from_centroids")
         return obj[0], obj[1], obj[2]
+
+    def kmeans_init(self, seed, max_iter=25, tol=1e-4):
+        """k-means++ / Lloyd on the resident Z_cos (hmy_kmeans_init).  Returns (K x d means, info dict)."""
+        Y = np.empty((self.K, self.d), dtype=np.float32)
+        info = (C.c_double * 3)()
+        self._ck(self.lib.hmy_kmeans_init(self.h, C.c_uint64(int(seed) & (2**64 - 1)), int(max_iter), float(tol), _ptr(Y), info),
+                 "hmy_kmeans_init")
+        return Y, {"iterations": int(info[0]), "inertia": float(info[1]), "last_shift2": float(info[2])}
 
     def kmeans_round(self, perm=None):
         obj = (C.c_double * 3)()

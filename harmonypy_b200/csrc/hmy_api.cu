@@ -21,6 +21,7 @@
 #include "hmy_round_tc5.cuh"
 #include "hmy_ridge.cuh"
 #include "hmy_ridge_mma.cuh"
+#include "hmy_kmeans_init.cuh"
 
 #define HMY_VERSION "harmony_b200 0.1.0 (sm_100a)"
 
@@ -580,6 +581,78 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
     swap_centroids(ctx);
     ctx->have_init = true;
     return fetch_obj(ctx, obj);
+}
+
+// ---- optional: k-means++ / Lloyd initialisation on the device (hmy_kmeans_init.cuh) -----------
+extern "C" int hmy_kmeans_init(hmy_ctx* ctx, uint64_t seed, int max_iter, double tol, float* Y_host, double info[3]) {
+    HmyDev& st = ctx->st;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_data) FAIL("hmy_kmeans_init: upload the data first");
+    if (st.Nglobal != st.N) FAIL("hmy_kmeans_init: single-GPU contexts only (with cells sharded over ranks pass init_centroids)");
+    if (!Y_host) FAIL("hmy_kmeans_init: NULL output");
+    if (max_iter < 0 || !(tol >= 0.0)) FAIL("hmy_kmeans_init: max_iter and tol must be non-negative");
+    if (st.N < st.K) FAIL("hmy_kmeans_init: fewer cells than clusters");
+    const int K = st.K, dp = st.dp;
+    const size_t smem_lloyd = ((size_t)K * (dp | 1) + K + (size_t)K * dp + (size_t)(HMY_KMI_THREADS / 32) * dp) * sizeof(float) + (size_t)K * sizeof(unsigned int);
+    if (smem_lloyd > 200 * 1024) FAIL("hmy_kmeans_init: K * d too large for the shared-memory Lloyd kernel (K (2 d + 2) floats <= 200 KB)");
+    CK(cudaFuncSetAttribute((const void*)k_lloyd_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lloyd));
+    float *mind2 = nullptr, *C = nullptr; unsigned long long* best = nullptr; double *sums = nullptr, *scal = nullptr; unsigned int* counts = nullptr;
+    std::vector<void*> tmp;
+    auto cleanup = [&]() { for (void* p : tmp) cudaFree(p); };
+#define KCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); char b_[512]; snprintf(b_, sizeof b_, "hmy_kmeans_init: %s failed: %s", #call, cudaGetErrorString(e_)); ctx->err = b_; return 1; } } while (0)
+    KCK(cudaMalloc((void**)&mind2, (size_t)st.N * sizeof(float))); tmp.push_back(mind2);
+    KCK(cudaMalloc((void**)&C, (size_t)K * dp * sizeof(float))); tmp.push_back(C);
+    KCK(cudaMalloc((void**)&best, (size_t)K * sizeof(unsigned long long))); tmp.push_back(best);
+    KCK(cudaMalloc((void**)&sums, (size_t)K * dp * sizeof(double))); tmp.push_back(sums);
+    KCK(cudaMalloc((void**)&counts, (size_t)K * sizeof(unsigned int))); tmp.push_back(counts);
+    KCK(cudaMalloc((void**)&scal, 4 * sizeof(double))); tmp.push_back(scal);
+    KCK(cudaMemsetAsync(best, 0xFF, (size_t)K * sizeof(unsigned long long), ctx->stream));
+    KCK(cudaMemsetAsync(C, 0, (size_t)K * dp * sizeof(float), ctx->stream));
+    // centre 0: uniform over the cells (by caller index, so the draw does not depend on the storage order)
+    const long long first_id = (long long)(hmy_splitmix64((unsigned long long)seed) % (unsigned long long)st.Nglobal);
+    int first_pos_i = 0;
+    KCK(cudaMemcpyAsync(&first_pos_i, st.pos_of + (first_id - st.cell_offset), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    KCK(cudaStreamSynchronize(ctx->stream));
+    const long long first_pos = first_pos_i;
+    const unsigned int grid = (unsigned int)std::min<long long>(4LL * ctx->sms, (st.N + (HMY_KMI_THREADS / 32) - 1) / (HMY_KMI_THREADS / 32));
+    for (int c = 1; c < K; ++c) {
+        k_kmpp_pass<<<grid, HMY_KMI_THREADS, dp * sizeof(float), ctx->stream>>>(st, best, first_pos, c, (unsigned long long)seed, mind2, best);
+        ctx->launches++;
+    }
+    KCK(cudaGetLastError());
+    {
+        std::vector<unsigned long long> hb(K);
+        KCK(cudaMemcpyAsync(hb.data(), best, (size_t)K * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        KCK(cudaStreamSynchronize(ctx->stream));
+        for (int c = 1; c < K; ++c)
+            if (hb[c] == ~0ull) { cleanup(); FAIL("hmy_kmeans_init: fewer distinct cells than clusters"); }
+    }
+    k_kmpp_gather<<<K, 64, 0, ctx->stream>>>(st, best, first_pos, C);
+    ctx->launches++;
+    KCK(cudaGetLastError());
+    double h[3] = {0.0, 0.0, 0.0};       // inertia | squared shift | mean feature variance
+    int iters = 0;
+    for (int it = 0; it < max_iter; ++it) {
+        KCK(cudaMemsetAsync(sums, 0, (size_t)K * dp * sizeof(double), ctx->stream));
+        KCK(cudaMemsetAsync(counts, 0, (size_t)K * sizeof(unsigned int), ctx->stream));
+        KCK(cudaMemsetAsync(scal, 0, 4 * sizeof(double), ctx->stream));
+        k_lloyd_assign<<<grid, HMY_KMI_THREADS, smem_lloyd, ctx->stream>>>(st, C, sums, counts, scal);
+        k_lloyd_update<<<1, 256, 0, ctx->stream>>>(st, C, sums, counts, scal + 1);
+        ctx->launches += 2;
+        KCK(cudaGetLastError());
+        KCK(cudaMemcpyAsync(h, scal, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        KCK(cudaStreamSynchronize(ctx->stream));
+        iters = it + 1;
+        if (h[1] <= tol * h[2]) break;                          // sklearn: centre shift^2 <= tol * mean(var(X, axis=0))
+    }
+    std::vector<float> Yp((size_t)K * dp);
+    KCK(cudaMemcpyAsync(Yp.data(), C, Yp.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    KCK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < K; ++k) for (int j = 0; j < st.d; ++j) Y_host[(size_t)k * st.d + j] = Yp[(size_t)k * dp + j];
+    if (info) { info[0] = (double)iters; info[1] = h[0]; info[2] = h[1]; }
+    cleanup();
+#undef KCK
+    return 0;
 }
 
 // ---- a3/a4/a5: one k-means round -----------------------------------------------------------

@@ -237,7 +237,7 @@ def run_harmony(data_mat, meta_data, vars_use, theta=None, lamb=None, sigma=0.1,
                 block_size=0.05, max_iter_harmony=10, max_iter_kmeans=20, epsilon_cluster=1e-5,
                 epsilon_harmony=1e-4, alpha=0.2, verbose=True, random_state=0, device=None, *,
                 init_centroids=None, perm_mode="reference", comm=None, engine_options=None,
-                engine_factory=None):
+                engine_factory=None, init_mode="sklearn"):
     """Run Harmony batch-effect correction on a B200 (drop-in for harmonypy.run_harmony).
 
     Parameters are those of harmonypy/harmony.py:49-67.  Additional keyword-only arguments:
@@ -251,6 +251,11 @@ def run_harmony(data_mat, meta_data, vars_use, theta=None, lamb=None, sigma=0.1,
         (no host work per round; use for large N).
     comm : torch.distributed process group (or True for the default group), optional
         Shard the cells over the ranks of the group (one process per GPU).
+    init_mode : "sklearn" | "device"
+        Where the k-means initialisation of harmony.py:369-373 runs when ``init_centroids`` is not given.
+        "sklearn" (default): exactly the reference's call.  "device": k-means++ / Lloyd on the GPU
+        (``hmy_kmeans_init``; same algorithm, its own random stream keyed by ``random_state``) -- for sizes
+        where sklearn dominates the wall time; single GPU only.
     """
     problem, vars_use = prepare_problem(data_mat, meta_data, vars_use, theta, lamb, sigma, nclust, tau)
     dev = get_device(device)
@@ -272,7 +277,7 @@ def run_harmony(data_mat, meta_data, vars_use, theta=None, lamb=None, sigma=0.1,
     np.random.seed(random_state)                                  # harmony.py:199
     return Harmony(problem, alpha, max_iter_harmony, max_iter_kmeans, epsilon_cluster, epsilon_harmony,
                    block_size, verbose, random_state, dev, init_centroids=init_centroids, perm_mode=perm_mode,
-                   comm=comm, engine_options=engine_options, engine_factory=engine_factory)
+                   comm=comm, engine_options=engine_options, engine_factory=engine_factory, init_mode=init_mode)
 
 
 class Harmony:
@@ -280,7 +285,7 @@ class Harmony:
 
     def __init__(self, problem, alpha, max_iter_harmony, max_iter_kmeans, epsilon_kmeans, epsilon_harmony,
                  block_size, verbose, random_state, device, init_centroids=None, perm_mode="reference",
-                 comm=None, engine_options=None, engine_factory=None, run=True):
+                 comm=None, engine_options=None, engine_factory=None, run=True, init_mode="sklearn"):
         self.problem = problem
         self.device = device
         self.N, self.B, self.d, self.K = problem.N, problem.B, problem.d, problem.K
@@ -297,6 +302,9 @@ class Harmony:
         if perm_mode not in ("reference", "device"):
             raise ValueError("perm_mode must be 'reference' or 'device'")
         self.perm_mode = perm_mode
+        if init_mode not in ("sklearn", "device"):
+            raise ValueError("init_mode must be 'sklearn' or 'device'")
+        self.init_mode = init_mode
         self._perm_gen = None
 
         if comm is True:
@@ -451,6 +459,12 @@ class Harmony:
     def init_cluster(self, random_state, init_centroids=None):
         """harmony.py:366-392.  k-means++ / Lloyd initialisation stays with sklearn on the host
         exactly as in the reference; everything after it runs on the device."""
+        if init_centroids is None and self.init_mode == "device":
+            if self.comm is not None and self.comm.world > 1:
+                raise ValueError("init_mode='device' runs on one GPU; with sharded cells pass init_centroids")
+            if self.verbose:
+                logger.info("Computing initial centroids on the device (k-means++ / Lloyd)...")
+            init_centroids, self.kmeans_init_info = self._engine.kmeans_init(int(random_state), max_iter=25, tol=1e-4)
         if init_centroids is None:
             if self.comm is None or self.comm.rank == 0:
                 from sklearn.cluster import KMeans

@@ -76,6 +76,15 @@ int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* codes_host);
  * (harmony.py:399-411; NOT yet multiplied by 2000/N). */
 int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0_host_Kxd, double obj[3]);
 
+/* Optional replacement of the sklearn call in init_cluster (harmony.py:369-373: KMeans(init="k-means++",
+ * n_init=1, max_iter=25) on the unit-length cells) for sizes where it dominates the wall time: k-means++
+ * seeding and Lloyd iterations on the resident Z_cos, stopped by sklearn's criterion (squared centre shift <=
+ * tol * mean feature variance) or after max_iter iterations.  It cannot reproduce sklearn's random stream:
+ * parity configurations keep sklearn and pass the centroids to hmy_init_from_centroids.  Single-GPU contexts.
+ * Y_host: K x d means (feed them to hmy_init_from_centroids); info: iterations run, inertia of the last
+ * assignment pass, last squared centre shift (may be NULL). */
+int hmy_kmeans_init(hmy_ctx* ctx, uint64_t seed, int max_iter, double tol, float* Y_host_Kxd, double info[3]);
+
 /* One iteration of the loop body of cluster() (harmony.py:443-453): centroid update,
  * cosine distances, blockwise update_R (harmony.py:464-513), objective.
  * perm_host: the n_global-long randperm of harmony.py:471 (int64, host) or NULL to draw a

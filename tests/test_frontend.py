@@ -86,3 +86,15 @@ def test_get_device_cuda_only():
     assert get_device(None) == 0 and get_device("cuda:3") == 3 and get_device("cuda") == 0
     with pytest.raises(ValueError):
         get_device("cpu")
+
+
+def test_mode_arguments_are_validated_before_any_device_work():
+    import pandas as pd
+    from harmonypy_b200.harmony import Harmony, prepare_problem
+    rng = np.random.default_rng(0)
+    Z = rng.normal(size=(60, 5)).astype(np.float32)
+    meta = pd.DataFrame({"b": pd.Categorical(rng.integers(0, 2, 60).astype(str))})
+    prob, _ = prepare_problem(pd.DataFrame(Z), meta, ["b"], nclust=4)
+    for kw in (dict(perm_mode="bogus"), dict(init_mode="bogus")):
+        with pytest.raises(ValueError, match="must be"):
+            Harmony(prob, 0.2, 1, 1, 1e-5, 1e-4, 0.05, False, 0, 0, run=False, **kw)

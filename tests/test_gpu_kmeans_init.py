@@ -1,0 +1,64 @@
+"""Device-side centroid initialisation (hmy_kmeans_init, Harmony(init_mode="device")) against its NumPy oracle and
+against the sklearn-initialised run.  Opt-in until the kernels have run on hardware once:
+
+    HMY_TEST_KMINIT=1 python -m pytest tests/test_gpu_kmeans_init.py -m gpu -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_case
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("HMY_TEST_KMINIT") != "1",
+                                 reason="k-means init kernels are opt-in until validated on hardware (HMY_TEST_KMINIT=1)")]
+
+
+def _harmony(inp, **kw):
+    from harmonypy_b200.harmony import Harmony, Problem
+    prob = Problem(Z=inp["Z"], codes=inp["codes"], levels=inp["levels"], level_names=[],
+                   Pr_b=inp["Pr_b"], theta=inp["theta"], lamb=inp["lamb"],
+                   lambda_estimation=bool(inp["lambda_estimation"]), sigma=inp["sigma"], K=int(inp["K"]))
+    return Harmony(prob, float(inp["alpha"]), int(inp["max_iter_harmony"]), int(inp["max_iter_kmeans"]),
+                   float(inp["epsilon_kmeans"]), float(inp["epsilon_harmony"]), float(inp["block_size"]), False,
+                   int(inp["random_state"]), 0, run=False, **kw)
+
+
+@pytest.mark.parametrize("name", ["pbmc", "synth", "ircolitis"])
+def test_seeding_and_lloyd_match_the_oracle(name):
+    from oracle.kmeans_init_oracle import kmeans_init
+    inp, _ = load_case(name)
+    ho = _harmony(inp)
+    K = int(inp["K"])
+    for seed in (0, 7):
+        seeds_gpu, _ = ho._engine.kmeans_init(seed, max_iter=0)
+        seeds_cpu, info0 = kmeans_init(inp["Z"], K, seed, max_iter=0)
+        np.testing.assert_allclose(seeds_gpu, seeds_cpu, atol=1e-6, err_msg="k-means++ picked different cells")
+        C_gpu, info = ho._engine.kmeans_init(seed, max_iter=25, tol=1e-4)
+        C_cpu, oinfo = kmeans_init(inp["Z"], K, seed, max_iter=25, tol=1e-4)
+        print(f"\n[{name} seed {seed}] iterations {info['iterations']} vs {oinfo['iterations']}, "
+              f"inertia {info['inertia']:.6f} vs {oinfo['inertia']:.6f}, max centre diff {np.abs(C_gpu - C_cpu).max():.2e}")
+        assert abs(info["iterations"] - oinfo["iterations"]) <= 1
+        assert abs(info["inertia"] - oinfo["inertia"]) <= 1e-3 * oinfo["inertia"]
+        assert np.abs(C_gpu - C_cpu).max() < 5e-3
+
+
+def test_harmony_with_device_init_lands_where_the_sklearn_run_does():
+    inp, gold = load_case("pbmc")
+    a = _harmony(inp, init_mode="device")
+    a.init_cluster(int(inp["random_state"]))
+    a.harmonize(int(inp["max_iter_harmony"]), False)
+    assert a.kmeans_init_info["iterations"] >= 1
+    # a different (equally good) initialisation: same objective level, not the same numbers
+    ref = float(gold["objective_harmony"][-1])
+    assert abs(a.objective_harmony[-1] - ref) < 0.03 * abs(ref)
+    assert np.isfinite(a.Z_corr).all()
+
+
+def test_sharded_or_missing_data_fail_loudly():
+    from harmonypy_b200._cabi import EngineError
+    inp, _ = load_case("synth")
+    ho = _harmony(inp)
+    with pytest.raises(EngineError, match="non-negative"):
+        ho._engine.kmeans_init(0, max_iter=-1)
