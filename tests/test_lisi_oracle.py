@@ -54,3 +54,26 @@ def test_simpson_edge_cases_follow_the_reference():
     D = np.full((k, n), 1e4) + np.arange(k)[:, None]
     s = compute_simpson(D, idx, codes, 2, 30.0)
     assert np.isfinite(s).all() and (s > 0).all()
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF, "harmonypy", "lisi.py")),
+                    reason="the reference checkout is only present in the build container")
+@pytest.mark.parametrize("n,d,perp,seed", [(600, 3, 30, 0), (900, 20, 15, 1), (500, 8, 42, 2)])
+def test_oracle_equals_live_reference_on_random_data(n, d, perp, seed):
+    import sys
+    sys.dont_write_bytecode = True
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    from harmonypy.lisi import compute_lisi as ref_lisi
+    rng = np.random.default_rng(seed)
+    t = rng.integers(0, 4, n)
+    X = rng.normal(size=(4, d))[t] * 2.5 + rng.normal(size=(n, d))
+    meta = pd.DataFrame({"type": pd.Categorical(t.astype(str)), "batch": pd.Categorical(rng.integers(0, 3, n).astype(str)),
+                         "one": pd.Categorical(["a"] * n)})
+    want = ref_lisi(X, meta, ["type", "batch", "one"], perp)
+    got = compute_lisi(X, meta, ["type", "batch", "one"], perp)
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    np.testing.assert_allclose(got[:, 2], 1.0, rtol=1e-12)          # a single category: LISI = 1 everywhere
