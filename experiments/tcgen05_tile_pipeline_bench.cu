@@ -21,6 +21,7 @@
 // are checked against a double-precision CPU evaluation at a smaller N first.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipe_bench experiments/tcgen05_tile_pipeline_bench.cu
+//   ./pipe_bench --hostcheck            # CPU: consistency of the generated work lists
 //   timeout 120 ./pipe_bench            # verify at N = 131072, then time at N = 1048576
 //
 // Compile-checked in the build container; NOT yet run on hardware.
@@ -520,7 +521,35 @@ static void launch_variant(int v, Dev& d) {
 }
 static void zero_slabs(Dev& d) { CK(cudaMemset(d.Ys, 0, (size_t)d.G * KM * DP * 4)); CK(cudaMemset(d.Os, 0, (size_t)d.G * KM * NB * 4)); }
 
+// CPU-only consistency check of the generated work lists (runs in the build container): every cell is in exactly one
+// tile, tiles are <= 128 cells of ONE CTA's share in ascending order, the last tile of every block is flagged
+static int hostcheck() {
+    const int N = 131072, G = 148;
+    Host h = make_host(N, G);
+    std::vector<int> seen(N, 0);
+    int bad = 0, flagged = 0;
+    for (int g = 0; g < G; ++g) {
+        const int c0 = (int)((long long)g * N / G), c1 = (int)((long long)(g + 1) * N / G);
+        for (int t = h.tile_first[g]; t < h.tile_first[g + 1]; ++t) {
+            const int nt = h.tile_nt[t] & 0xFFFF, off = h.tile_off[t];
+            if (nt < 1 || nt > TILE) ++bad;
+            flagged += (h.tile_nt[t] >> 30) & 1;
+            for (int i = 0; i < nt; ++i) {
+                const int c = h.list[off + i];
+                if (c < c0 || c >= c1) ++bad;
+                if (i > 0 && c <= h.list[off + i - 1]) ++bad;
+                seen[c]++;
+            }
+        }
+    }
+    for (int c = 0; c < N; ++c) if (seen[c] != 1) ++bad;
+    for (int i = 0; i < N; ++i) if (h.lev[i] < 0 || h.lev[i] >= NLEV) ++bad;
+    printf("hostcheck: %d cells, %d tiles, %d block-final tiles (<= %d), %s\n", N, (int)h.tile_off.size(), flagged, G * NBLK, bad ? "FAIL" : "PASS");
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
+    if (argc > 1 && !strcmp(argv[1], "--hostcheck")) return hostcheck();
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int G = prop.multiProcessorCount;
     const char* names[4] = {"v1 (fp32 gather, synchronous)", "presplit cp.async, synchronous", "presplit cp.async, pipelined", "pipelined, 256 threads"};
