@@ -56,7 +56,7 @@ def test_harmony_with_device_init_lands_where_the_sklearn_run_does():
     assert np.isfinite(a.Z_corr).all()
 
 
-def test_sharded_or_missing_data_fail_loudly():
+def test_bad_arguments_fail_loudly():
     from harmonypy_b200._cabi import EngineError
     inp, _ = load_case("synth")
     ho = _harmony(inp)
