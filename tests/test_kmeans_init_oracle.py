@@ -2,7 +2,6 @@
 k-means++ / Lloyd?  Compared with sklearn -- the reference's initialiser, harmony.py:369-373 -- on the reference's own
 pbmc PCs.  CPU only."""
 import numpy as np
-import pytest
 
 from conftest import load_case
 from oracle.kmeans_init_oracle import kmeans_init, kmeanspp_seed, splitmix64, uniform

@@ -8,7 +8,6 @@ centroids and the same permutation stream.  Agreement is at rounding level (1e-9
 
 Runs only where /root/reference exists (the build container); skipped on the GPU box.  CPU only.
 """
-import importlib.util
 import os
 import sys
 
