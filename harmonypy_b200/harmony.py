@@ -327,6 +327,10 @@ class Harmony:
 
         factory = engine_factory or _cuda_engine_factory
         self._engine = factory(problem, self._lo, self._hi, device, comm, engine_options)
+        if perm_mode == "device" and "seed" not in (engine_options or {}):
+            # the device-side permutation follows random_state like the host stream does (harmony.py:200);
+            # random_state = 0 is the library's default key
+            self._engine.set_option("seed", int(random_state))
         lamb = problem.lamb if not problem.lambda_estimation else None
         self._engine.set_params(problem.Pr_b, problem.theta, problem.sigma, lamb, problem.lambda_estimation,
                                 alpha, block_size)

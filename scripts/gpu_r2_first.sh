@@ -26,3 +26,4 @@ done
 HMY_ENGINE_OPTS=tc5=1 timeout 300 python scripts/trace_round.py syn1m > gpurun_out/trace_tc5.txt 2>&1; echo "trace tc5 exit $?"; tail -24 gpurun_out/trace_tc5.txt
 HMY_TEST_LISI=1 timeout 300 python -m pytest tests/test_gpu_lisi.py -m gpu -x -q > gpurun_out/pytest_lisi.log 2>&1; echo "pytest lisi exit $?"; tail -5 gpurun_out/pytest_lisi.log
 HMY_TEST_KMINIT=1 timeout 300 python -m pytest tests/test_gpu_kmeans_init.py -m gpu -x -q -s > gpurun_out/pytest_kminit.log 2>&1; echo "pytest kminit exit $?"; grep -E "^\[|passed|failed|Error|assert" gpurun_out/pytest_kminit.log | tail -12
+HMY_TEST_DEVPERM=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -k replayed_through_the_oracle -x -q -s > gpurun_out/pytest_devperm.log 2>&1; echo "pytest devperm exit $?"; grep -E "^\[|passed|failed|Error|assert" gpurun_out/pytest_devperm.log | tail -6

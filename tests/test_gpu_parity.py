@@ -153,6 +153,35 @@ def test_tc5_refuses_unsupported_shapes_loudly():
         _engine_run(inp, options={"tc5": 1}, record=False, max_iter=0)
 
 
+@pytest.mark.skipif(os.environ.get("HMY_TEST_DEVPERM") != "1",
+                    reason="opt-in until the NumPy mirror of the device permutation has been compared with the GPU once (HMY_TEST_DEVPERM=1)")
+@pytest.mark.parametrize("seed", [0, 11])
+def test_device_permutation_run_replayed_through_the_oracle(seed):
+    """perm_mode="device": the engine's own block permutation, mirrored in NumPy (oracle/device_perm.py), lets the
+    fp64 oracle replay exactly the run the bench workloads use -- parity is no longer tied to the host stream."""
+    import pandas as pd
+    from harmonypy_b200.harmony import Harmony, prepare_problem
+    from harmonypy_b200.synthetic import make_synthetic
+    from oracle.device_perm import device_perm
+    N, d, K = 20000, 50, 100
+    Z, meta = make_synthetic(N, d, [20], seed=3)
+    prob, _ = prepare_problem(pd.DataFrame(Z), meta, list(meta.columns), nclust=K)
+    Y0 = Z[np.random.default_rng(1).choice(N, K, replace=False)]
+    ho = Harmony(prob, 0.2, 2, 6, 1e-5, 1e-4, 0.05, False, seed, 0, perm_mode="device", run=False)
+    orc = _oracle_for(prob, max_iter_kmeans=6)
+    ho.init_cluster(seed, Y0)
+    orc.init_from_centroids(Y0.T)
+    counter = iter(range(10 ** 6))
+    for _ in range(2):
+        ho.cluster(); ho.moe_correct_ridge()
+        orc.cluster(lambda: device_perm(N, seed, next(counter))); orc.moe_correct_ridge()
+    assert list(ho.kmeans_rounds) == list(orc.kmeans_rounds)
+    print(f"\n[device perm, seed {seed}] Z_corr {rel_max(ho.Z_corr, orc.Z_corr.T):.3e} R {rel_max(ho.R, orc.R.T):.3e}")
+    assert rel_max(ho.Z_corr, orc.Z_corr.T) < 1e-4
+    assert rel_max(ho.R, orc.R.T) < 1e-3
+    np.testing.assert_allclose(ho.objective_kmeans, orc.objective_kmeans, rtol=5e-5)
+
+
 def _oracle_for(prob, dtype=np.float64, **kw):
     from oracle.harmony_oracle import HarmonyOracle, onehot_from_codes
     return HarmonyOracle(prob.Z.T, onehot_from_codes(prob.codes, prob.levels, dtype), prob.Pr_b, prob.sigma,
