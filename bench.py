@@ -358,7 +358,11 @@ def run_ours(args, w):
             traffic = tj.get("k_round_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_round (one k-means round, persistent cooperative kernel)",
+    tc5 = eng.counter("tc5") == 1
+    if tc5:
+        traffic = None                      # profiles/traffic.json was captured for k_round_mma
+    roofline = {"bound": "hbm", "kernel": ("k_round_tc5 (tcgen05 / tensor-memory round kernel, opt-in)" if tc5 else
+                                           "k_round (one k-means round, persistent cooperative kernel)"),
                 "achieved": ach_round, "peak": peak, "unit": "GB/s", "frac": ach_round / peak, "traffic": traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": b_round,
                 "bytes_per_launch": b_round * n_local, "avg_launch_ms": ms_round / max(n_rounds, 1),
