@@ -35,6 +35,9 @@
 #include <cstring>
 #include <vector>
 
+#ifndef ABL
+#define ABL 0      // ablation bit mask (timing runs only): 1 no HBM R store, 2 no R operand (smem) store, 4 no lg2 term,
+#endif             // 8 no ex2, 16 no accumulation MMAs, 32 no Z gather, 64 no scoring MMAs
 constexpr int TILE = 128, DP = 64, DPF = 52, D = 50, K = 100, KP = 112, KM = 128, NB = 32, NLEV = 8, NBLK = 20;
 constexpr float OPSCALE = 1024.f, ACCSCALE = 1.f / 1048576.f;
 constexpr int TMEM_COLS = 512;                 // D1[0]: [0,112)  D1[1]: [128,240)  D2y: [256,320)  D2o: [320,352)
@@ -247,7 +250,7 @@ __global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
 #pragma unroll
             for (int u = 0; u < 2048 / NTHR; ++u) {
                 const int q = tid + u * NTHR, row = q >> 4, ch = q & 15;
-                if (row < nt) {
+                if (row < nt && !(ABL & 32)) {
                     const int cell = a.list[off + row];
                     const uint32_t dst = smem_u32((ch < 8 ? Zh : Zl) + (row >> 3) * Z_SBO_K + (ch & 7) * Z_LBO_K + (row & 7) * 16);
                     cp_async16(dst, a.Zs + (size_t)cell * (2 * DP) + ch * 8);
@@ -259,7 +262,7 @@ __global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
     auto issue_score = [&](int b, int d1) {       // buffer b -> D1[d1]
         if (tid == 0) {
             const uint32_t zh = sb + b * 2 * SZ, zl = zh + SZ;
-            for (int ks = 0; ks < DP / 16; ++ks) {
+            for (int ks = 0; ks < ((ABL & 64) ? 0 : DP / 16); ++ks) {
                 const uint32_t o = ks * 2 * Z_LBO_K;
                 const uint64_t dzh = make_desc(zh + o, Z_LBO_K, Z_SBO_K), dzl = make_desc(zl + o, Z_LBO_K, Z_SBO_K);
                 const uint64_t dyh = make_desc(smem_u32(sYh) + o, Y_LBO, Y_SBO), dyl = make_desc(smem_u32(sYl) + o, Y_LBO, Y_SBO);
@@ -274,7 +277,7 @@ __global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
         if (tid == 0) {
             const uint32_t zh = sb + b * 2 * SZ, zl = zh + SZ, ot = smem_u32(sO) + b * SO;
             const int ksteps = (nt + 15) >> 4;
-            for (int ks = 0; ks < ksteps; ++ks) {
+            for (int ks = 0; ks < ((ABL & 16) ? 0 : ksteps); ++ks) {
                 const uint64_t rh = make_desc(smem_u32(sRh) + ks * 2 * R_LBO, R_LBO, R_SBO), rl = make_desc(smem_u32(sRl) + ks * 2 * R_LBO, R_LBO, R_SBO);
                 const uint64_t dzh = make_desc(zh + ks * 2 * Z_LBO_MN, Z_LBO_MN, Z_SBO_MN), dzl = make_desc(zl + ks * 2 * Z_LBO_MN, Z_LBO_MN, Z_SBO_MN);
                 const uint64_t dot = make_desc(ot + ks * 2 * O_LBO, O_LBO, O_SBO);
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const float t = fmaf(-acc[e], k1v[e], k1v[e] * 1048576.0f);
-                const float s = (col + e < K) ? ex2_approx(-t) : 0.f;
+                const float s = (col + e < K) ? ((ABL & 8) ? fmaf(t, -1e-3f, 1.0f) : ex2_approx(-t)) : 0.f;
                 ss += s;
                 const float ev = s * pv[e];
                 sp += ev;
@@ -348,7 +351,8 @@ __global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 r[j] = E[c0 + j] * sc;
-                oe = fmaf(k3v[j], (r[j] > 0.f ? r[j] * lg2_approx(r[j]) : 0.f), oe);
+                if (!(ABL & 4)) oe = fmaf(k3v[j], (r[j] > 0.f ? r[j] * lg2_approx(r[j]) : 0.f), oe);
+                else oe = fmaf(k3v[j], r[j], oe);
             }
             uint4 hi, lo;
             split2(r[0] * OPSCALE, r[1] * OPSCALE, hi.x, lo.x);
@@ -356,13 +360,15 @@ __global__ void __launch_bounds__(NTHR, 1) tile_pipeline(Args a) {
             split2(r[4] * OPSCALE, r[5] * OPSCALE, hi.z, lo.z);
             split2(r[6] * OPSCALE, r[7] * OPSCALE, hi.w, lo.w);
             const int off = ((cb + c0) >> 3) * R_SBO + (ct >> 3) * R_LBO + (ct & 7) * 16;
-            *reinterpret_cast<uint4*>(sRh + off) = hi;
-            *reinterpret_cast<uint4*>(sRl + off) = lo;
+            if (!(ABL & 2)) {
+                *reinterpret_cast<uint4*>(sRh + off) = hi;
+                *reinterpret_cast<uint4*>(sRl + off) = lo;
+            } else if (hi.x == 0x12345u && lo.y == 0x54321u) objd += 1.f;
         }
         if (valid) { objd += sc * sd; obje += oe; }
     };
     auto store_row = [&](int cell, bool valid) {
-        if (!valid) return;
+        if (!valid || (ABL & 1)) return;
         float* Rg = a.R + (size_t)cell * KP + cb;
 #pragma unroll
         for (int c0 = 0; c0 < CW; c0 += 4)
@@ -554,6 +560,9 @@ int main(int argc, char** argv) {
     const int G = prop.multiProcessorCount;
     const char* names[4] = {"v1 (fp32 gather, synchronous)", "presplit cp.async, synchronous", "presplit cp.async, pipelined", "pipelined, 256 threads"};
     int bad = 0;
+    const bool time_only = (argc > 1 && !strcmp(argv[1], "--time-only"));
+    const int only_mode = (time_only && argc > 2) ? atoi(argv[2]) : -1;
+    if (!time_only)
     {   // ---- correctness at a small N (every tile ragged) and at a medium N against fp64
         const int N = (argc > 1) ? atoi(argv[1]) : 131072;
         Host h = make_host(N, G);
@@ -600,6 +609,7 @@ int main(int argc, char** argv) {
         const int tiles = (int)h.tile_off.size();
         cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
         for (int mode = 0; mode < 4; ++mode) {
+            if (only_mode >= 0 && mode != only_mode) continue;
             zero_slabs(d); launch_variant(mode, d); CK(cudaDeviceSynchronize());
             float best = 1e30f, sum = 0;
             for (int it = 0; it < 5; ++it) {
@@ -610,7 +620,7 @@ int main(int argc, char** argv) {
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); best = fminf(best, ms); sum += ms;
             }
             const double bytes = (double)N * (KP * 4 + (mode == 0 ? DPF * 4 : 2 * DP * 2) + 8);
-            printf("N=%d  %-34s %.1f us per pass (best %.1f), %.2f us per tile and SM, %.0f GB/s of R + Z traffic\n", N, names[mode],
+            printf("ABL=%d N=%d  %-34s %.1f us per pass (best %.1f), %.2f us per tile and SM, %.0f GB/s of R + Z traffic\n", ABL, N, names[mode],
                    1e3 * sum / 5, 1e3 * best, 1e3 * (sum / 5) / ((double)tiles / G), bytes / (sum / 5 * 1e-3) / 1e9);
         }
         free_device(d);

@@ -1,18 +1,12 @@
 """Device-side centroid initialisation (hmy_kmeans_init, Harmony(init_mode="device")) against its NumPy oracle and
-against the sklearn-initialised run.  Opt-in until the kernels have run on hardware once:
-
-    HMY_TEST_KMINIT=1 python -m pytest tests/test_gpu_kmeans_init.py -m gpu -q
+against the sklearn-initialised run (validated on a B200 in round 2; runs with the plain `-m gpu` suite).
 """
-import os
-
 import numpy as np
 import pytest
 
 from conftest import load_case
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("HMY_TEST_KMINIT") != "1",
-                                 reason="k-means init kernels are opt-in until validated on hardware (HMY_TEST_KMINIT=1)")]
+pytestmark = [pytest.mark.gpu]
 
 
 def _harmony(inp, **kw):
@@ -41,7 +35,12 @@ def test_seeding_and_lloyd_match_the_oracle(name):
               f"inertia {info['inertia']:.6f} vs {oinfo['inertia']:.6f}, max centre diff {np.abs(C_gpu - C_cpu).max():.2e}")
         assert abs(info["iterations"] - oinfo["iterations"]) <= 1
         assert abs(info["inertia"] - oinfo["inertia"]) <= 1e-3 * oinfo["inertia"]
-        assert np.abs(C_gpu - C_cpu).max() < 5e-3
+        # Lloyd is chaotic in the assignments of near-tied cells (fp32 device sums vs fp64 oracle sums): after 25
+        # iterations on 69k cells single cells have changed sides (measured: centres 1.9e-2 apart at equal inertia),
+        # so the centres themselves are compared after ONE iteration, where only exact near-ties can differ
+        C1_gpu, _ = ho._engine.kmeans_init(seed, max_iter=1, tol=0.0)
+        C1_cpu, _ = kmeans_init(inp["Z"], K, seed, max_iter=1, tol=0.0)
+        assert np.abs(C1_gpu - C1_cpu).max() < 5e-3
 
 
 def test_harmony_with_device_init_lands_where_the_sklearn_run_does():

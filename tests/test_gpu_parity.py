@@ -109,14 +109,7 @@ def test_tensor_core_round_matches_simt_round():
     np.testing.assert_allclose(a.objective_kmeans, b.objective_kmeans, rtol=2e-6)
 
 
-# The tcgen05 / tensor-memory round kernel (engine option "tc5", hmy_round_tc5.cuh) was written after round 1's
-# GPU budget was spent: until it has been validated on a B200 it is opt-in here as well.
-#   HMY_TEST_TC5=1 python -m pytest tests/test_gpu_parity.py -m gpu -k tc5
-_tc5 = pytest.mark.skipif(os.environ.get("HMY_TEST_TC5") != "1",
-                          reason="tensor-memory round kernel is opt-in until validated on hardware (HMY_TEST_TC5=1)")
-
-
-@_tc5
+# The tcgen05 / tensor-memory round kernel (engine option "tc5", hmy_round_tc5.cuh): validated on a B200 in round 2.
 @pytest.mark.parametrize("name", ["synth", "pbmc"])
 def test_tc5_round_matches_mma_round_and_golden(name):
     """K = 40 / two covariates (NC = 4) and K = 100 / one covariate (NC = 7), ragged last tiles, 20 blocks."""
@@ -134,7 +127,6 @@ def test_tc5_round_matches_mma_round_and_golden(name):
     np.testing.assert_allclose(a.objective_kmeans, b.objective_kmeans, rtol=2e-6)
 
 
-@_tc5
 def test_tc5_round_ircolitis_final():
     inp, gold = load_case("ircolitis")
     ho, _ = _engine_run(inp, options={"tc5": 1}, record=False)
@@ -143,7 +135,6 @@ def test_tc5_round_ircolitis_final():
     assert rel_max(ho.Z_corr[gold["final_cells"]], gold["Zcorr_final"]) < 1e-4
 
 
-@_tc5
 def test_tc5_refuses_unsupported_shapes_loudly():
     from harmonypy_b200._cabi import EngineError
     inp, _ = load_case("synth")
@@ -153,8 +144,6 @@ def test_tc5_refuses_unsupported_shapes_loudly():
         _engine_run(inp, options={"tc5": 1}, record=False, max_iter=0)
 
 
-@pytest.mark.skipif(os.environ.get("HMY_TEST_DEVPERM") != "1",
-                    reason="opt-in until the NumPy mirror of the device permutation has been compared with the GPU once (HMY_TEST_DEVPERM=1)")
 @pytest.mark.parametrize("seed", [0, 11])
 def test_device_permutation_run_replayed_through_the_oracle(seed):
     """perm_mode="device": the engine's own block permutation, mirrored in NumPy (oracle/device_perm.py), lets the
