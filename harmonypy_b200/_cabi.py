@@ -31,6 +31,7 @@ SYMBOLS = {
     "hmy_init_from_centroids": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_kmeans_init": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_kmeans_round": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
+    "hmy_queue_perm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmy_ridge_correct": (C.c_int, [C.c_void_p]),
     "hmy_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "hmy_synchronize": (C.c_int, [C.c_void_p]),
@@ -154,6 +155,21 @@ class Engine:
             p = _ptr(perm)
         self._ck(self.lib.hmy_kmeans_round(self.h, p, obj), "hmy_kmeans_round")
         return obj[0], obj[1], obj[2]
+
+    @property
+    def lookahead(self):
+        """True when the context runs the block permutations one round ahead (tensor-memory round kernel): the
+        first round's permutation is queued before init, every round call carries the NEXT round's."""
+        return self.counter("lookahead") == 1
+
+    def queue_perm(self, perm=None):
+        if perm is None:
+            p = None
+        else:
+            perm = np.ascontiguousarray(perm, dtype=np.int64)
+            assert perm.shape == (self.n_global,)
+            p = _ptr(perm)
+        self._ck(self.lib.hmy_queue_perm(self.h, p), "hmy_queue_perm")
 
     def ridge_correct(self):
         self._ck(self.lib.hmy_ridge_correct(self.h), "hmy_ridge_correct")

@@ -40,10 +40,21 @@ struct hmy_ctx {
     bool use_mma = false, want_mma = true, ridge_mma = false, want_ridge_mma = true;
     float zscale = 1.f;
     int force_wn = 0;
-    // opt-in tcgen05 / tensor-memory round kernel (hmy_round_tc5.cuh)
-    bool want_tc5 = false, use_tc5 = false;
+    // tcgen05 / tensor-memory round kernel (hmy_round_tc5.cuh): the single-GPU persistent path where its shape
+    // limits hold.  want_tc5: -1 auto (default), 0 off, 1 required (unsupported shapes fail)
+    int want_tc5 = -1;
+    bool tc5_ok = false;                    // shape supported (decided in plan_round)
+    bool t5_state = false;                  // the device tables (running O, removed sums) were produced by that kernel
     int tc5_nc = 0, smem_tc5 = 0, G_tc5 = 0;
-    const void* fn_tc5 = nullptr; const void* fn_tc5_fused = nullptr;
+    const void* fn_tc5 = nullptr;
+    unsigned char* blkbuf[2] = {nullptr, nullptr};      // block of every cell: round r in blkbuf[r & 1]
+    float* t5_told[2] = {nullptr, nullptr}; int told_cur = 0;     // [nblk][B][K] removed sums | [nblk][K] their row sums
+    float* t5_dnew = nullptr;                                      // [nblk][B][K] re-added sums | [nblk][K] row sums
+    size_t t5_table_floats = 0;
+    double* t5_rsum[2] = {nullptr, nullptr}; int rsum_cur = 0;
+    unsigned long long bar_count64 = 0;     // host mirror of the device grid-barrier counter
+    long long n_assigned = 0, n_done = 0;   // rounds (since init) with a block assignment / executed
+    int write_r = 1; bool r_valid = true;   // R rows in HBM are those of the last stage
     int G = 0, sms = 0;
     int smem_round = 0, smem_mom = 0, smem_apply = 0, smem_solve = 0;
     int grid_ridge = 0, grid_mom = 0, ridge_threads = HMY_THREADS;
@@ -116,6 +127,8 @@ HMY_DECL_BIND(8, 4) HMY_DECL_BIND(8, 8) HMY_DECL_BIND(8, 16)
 HMY_DECL_BIND_MMA(4, 1) HMY_DECL_BIND_MMA(8, 1) HMY_DECL_BIND_MMA(14, 1) HMY_DECL_BIND_MMA(16, 1)
 HMY_DECL_BIND_MMA(8, 2) HMY_DECL_BIND_MMA(14, 2) HMY_DECL_BIND_MMA(16, 2)
 
+static inline bool use_tc5(const hmy_ctx* ctx);
+static int split_zcos(hmy_ctx* ctx);
 extern "C" void hmy_bind_tc5_4(const void** fns);
 extern "C" void hmy_bind_tc5_7(const void** fns);
 extern "C" void hmy_bind_tc5_8(const void** fns);
@@ -219,6 +232,16 @@ static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_glob
     if (dev_alloc(ctx, &st.bar_count, 2)) return 1;
     st.bar_gen = st.bar_count + 1;
     CK(cudaMemset(st.bar_count, 0, 2 * sizeof(unsigned int)));
+    if (dev_alloc(ctx, &st.bar64, 1)) return 1;
+    CK(cudaMemset(st.bar64, 0, sizeof(unsigned long long)));
+    if (K <= 128 && d <= 64) {
+        // operands of the tensor-memory round kernel: pre-split Z_cos rows, annotated lists, two block-id buffers
+        const int dt = (d + 15) / 16;
+        if (dev_alloc(ctx, &st.Zs16, (size_t)st.N * 32 * dt)) return 1;
+        if (dev_alloc(ctx, &st.list2, (size_t)st.N)) return 1;
+        if (dev_alloc(ctx, &ctx->blkbuf[0], (size_t)st.N)) return 1;
+        if (dev_alloc(ctx, &ctx->blkbuf[1], (size_t)st.N)) return 1;
+    }
     CK(cudaMemset(st.O, 0, (size_t)B * K * sizeof(double)));
     CK(cudaMemset(st.W, 0, (size_t)B * K * st.dp * sizeof(float)));
     // ridge accumulators in one zeroable block: Gram | Mom
@@ -297,23 +320,30 @@ static int plan_round(hmy_ctx* ctx) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, ctx->round_threads, ctx->smem_round));
     if (nb < 1) FAIL("round kernel does not fit on an SM");
     ctx->G = nb * ctx->sms;
-    ctx->use_tc5 = false;
-    if (ctx->want_tc5) {
-        // fail loudly: the option asks for this kernel, there is no silent fallback to another one
-        if (!ctx->use_mma || st.K > 128 || st.d > 64 || st.B > TC5_NB || nblk > 32)
-            FAIL("option tc5: the tensor-memory round kernel needs K <= 128, d <= 64, B <= 32 and at most 32 blocks");
-        const void* f[2] = {nullptr, nullptr};
-        if (st.K <= 64) { hmy_bind_tc5_4(f); ctx->tc5_nc = 4; } else if (st.K <= 112) { hmy_bind_tc5_7(f); ctx->tc5_nc = 7; } else { hmy_bind_tc5_8(f); ctx->tc5_nc = 8; }
-        ctx->fn_tc5 = f[0]; ctx->fn_tc5_fused = f[1];
-        ctx->smem_tc5 = tc5_smem_plan(st.B, ctx->tc5_nc).total;
-        if (ctx->smem_tc5 > 226 * 1024) FAIL("option tc5: round kernel needs more than 226 KB of shared memory");
-        CK(cudaFuncSetAttribute(ctx->fn_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
-        CK(cudaFuncSetAttribute(ctx->fn_tc5_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
-        int nt5 = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt5, ctx->fn_tc5, TC5_TILE, ctx->smem_tc5));
-        if (nt5 < 1) FAIL("option tc5: round kernel does not fit on an SM");
-        ctx->G_tc5 = ctx->sms;            // one CTA per SM: each holds 256 of the SM's 512 tensor-memory columns
-        ctx->use_tc5 = true;
+    ctx->tc5_ok = false;
+    if (ctx->want_tc5 != 0) {
+        const bool shape = st.K <= 128 && st.d <= 64 && nblk <= 32 && st.B <= 65535 && st.Zs16 != nullptr;
+        // option tc5 = 1 asks for this kernel: unsupported shapes fail loudly, there is no silent fallback then
+        if (!shape && ctx->want_tc5 == 1)
+            FAIL("option tc5: the tensor-memory round kernel needs K <= 128, d <= 64 and at most 32 blocks");
+        if (shape) {
+            const void* f[2] = {nullptr, nullptr};
+            if (st.K <= 64) { hmy_bind_tc5_4(f); ctx->tc5_nc = 4; } else if (st.K <= 112) { hmy_bind_tc5_7(f); ctx->tc5_nc = 7; } else { hmy_bind_tc5_8(f); ctx->tc5_nc = 8; }
+            ctx->fn_tc5 = f[0];
+            ctx->smem_tc5 = t5_smem_bytes(ctx->tc5_nc);
+            CK(cudaFuncSetAttribute(ctx->fn_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
+            int nt5 = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt5, ctx->fn_tc5, T5_THREADS, ctx->smem_tc5));
+            if (nt5 < 1) FAIL("tensor-memory round kernel does not fit on an SM");
+            ctx->G_tc5 = ctx->sms;            // one CTA per SM: it owns the SM's tensor memory
+            ctx->t5_table_floats = (size_t)nblk * st.B * st.K + (size_t)nblk * st.K;
+            for (int i = 0; i < 2; ++i) {
+                if (dev_alloc(ctx, &ctx->t5_told[i], ctx->t5_table_floats)) return 1;
+                if (dev_alloc(ctx, &ctx->t5_rsum[i], (size_t)st.K)) return 1;
+            }
+            if (dev_alloc(ctx, &ctx->t5_dnew, ctx->t5_table_floats)) return 1;
+            ctx->tc5_ok = true;
+        }
     }
     // per-round zero block: Told | Dnew | Yacc is separate (ridge also uses it) | obj
     const size_t nT = (size_t)nblk * st.B * st.K;
@@ -472,6 +502,7 @@ extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* co
     }
     cudaFree(raw);
     CK(e);
+    if (split_zcos(ctx)) return 1;
     lap("malloc + H2D + ingest + free");
     ctx->have_data = true;
     return 0;
@@ -542,9 +573,77 @@ static int staged_round(hmy_ctx* ctx, int what, int blk) {
 // the persistent round kernel (cooperative launch): tensor-memory version when option "tc5" selected it
 static int launch_persistent(hmy_ctx* ctx, void** args) {
     const bool fk = ctx->fused || ctx->force_fused_kernel;
-    if (ctx->use_tc5)
-        return launch(ctx, fk ? ctx->fn_tc5_fused : ctx->fn_tc5, dim3(ctx->G_tc5), dim3(TC5_TILE), args, ctx->smem_tc5, true);
     return launch(ctx, fk ? ctx->fn_round_fused : ctx->fn_round, dim3(ctx->G), dim3(ctx->round_threads), args, ctx->smem_round, true);
+}
+
+
+// ---- tensor-memory round kernel: host side ----------------------------------------------------------------------
+// It is the path of single-GPU persistent runs whose shape it supports; sharded runs (all-reduce callback or
+// peer exchange) and launch-per-block mode stay on the mma.sync / SIMT kernels.
+static inline bool use_tc5(const hmy_ctx* ctx) { return ctx->tc5_ok && ctx->persistent && !ctx->ar && !ctx->fused; }
+
+static int split_zcos(hmy_ctx* ctx) {
+    HmyDev& st = ctx->st;
+    if (!st.Zs16) return 0;
+    const long long threads = st.N * 8 * ((st.d + 15) / 16);
+    k_split_zcos<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(st);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// block of every cell in round `round` (since init) -> blkbuf[round & 1]  (harmony.py:471-475, :483-484)
+static int assign_round(hmy_ctx* ctx, const int64_t* perm_host, long long round) {
+    HmyDev s = ctx->st;
+    s.blk = ctx->blkbuf[round & 1];
+    if (perm_host) {
+        if (!ctx->d_perm) CK(cudaMalloc((void**)&ctx->d_perm, (size_t)s.Nglobal * sizeof(long long)));
+        CK(cudaMemcpyAsync(ctx->d_perm, perm_host, (size_t)s.Nglobal * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        k_assign_from_perm<<<(unsigned int)((s.Nglobal + 255) / 256), 256, 0, ctx->stream>>>(s, ctx->d_perm);
+    } else {
+        int hb = 1;
+        while ((1ull << (2 * hb)) < (unsigned long long)s.Nglobal) ++hb;
+        k_assign_feistel<<<(unsigned int)((s.N + 255) / 256), 256, 0, ctx->stream>>>(s, ctx->seed, ctx->round_counter, hb);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    ctx->round_counter++;
+    ctx->n_assigned = round + 1;
+    return 0;
+}
+
+extern "C" int hmy_queue_perm(hmy_ctx* ctx, const int64_t* perm_host) {
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_data || !ctx->have_params) FAIL("hmy_queue_perm: set params and data first");
+    if (!use_tc5(ctx)) FAIL("hmy_queue_perm: this context does not run one round ahead (counter \"lookahead\" is 0): pass the permutation to hmy_kmeans_round");
+    if (ctx->n_assigned > ctx->n_done + (ctx->have_init ? 1 : 0)) FAIL("hmy_queue_perm: the next round already has its permutation");
+    return assign_round(ctx, perm_host, ctx->n_assigned);
+}
+
+static int launch_tc5(hmy_ctx* ctx, int mode) {
+    HmyDev s = ctx->st;
+    const long long r = ctx->n_done;
+    s.Told = ctx->t5_told[ctx->told_cur]; s.Told_next = ctx->t5_told[ctx->told_cur ^ 1];
+    s.Rsum = ctx->t5_rsum[ctx->rsum_cur]; s.Rsum_next = ctx->t5_rsum[ctx->rsum_cur ^ 1];
+    s.Dnew = ctx->t5_dnew;
+    s.write_R = ctx->write_r;
+    if (mode == 1) { s.blk_next = ctx->blkbuf[0]; s.Told = nullptr; s.Told_next = ctx->t5_told[ctx->told_cur]; }
+    else { s.blk = ctx->blkbuf[r & 1]; s.blk_next = ctx->blkbuf[(r + 1) & 1]; }
+    unsigned long long base = ctx->bar_count64;
+    void* args[] = {&s, &mode, &base};
+    if (launch(ctx, ctx->fn_tc5, dim3(ctx->G_tc5), dim3(T5_THREADS), args, ctx->smem_tc5, true)) return 1;
+    ctx->bar_count64 += (unsigned long long)ctx->G_tc5 * (unsigned long long)(mode == 1 ? 1 : s.nblk);
+    ctx->r_valid = ctx->write_r != 0;
+    ctx->t5_state = true;
+    return 0;
+}
+
+// objective sums of the last tc5 stage: the kernel leaves them in obj[0..2]
+static int fetch_obj_tc5(hmy_ctx* ctx, double obj[3]) {
+    CK(cudaMemcpyAsync(ctx->h_obj, ctx->st.obj, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (obj) { obj[0] = ctx->h_obj[0]; obj[1] = ctx->h_obj[1]; obj[2] = ctx->h_obj[2]; }
+    return 0;
 }
 
 // ---- a2: init ------------------------------------------------------------------------------
@@ -562,6 +661,24 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
     }
     CK(cudaMemcpyAsync(st.Yhat, Y.data(), Y.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));          // Y is a stack-lifetime host buffer
+    if (use_tc5(ctx)) {
+        // the init assignment also accumulates the sums the FIRST round's blocks remove: it needs that round's blocks
+        if (st.ncombo >= (1 << 23)) FAIL("too many covariate combinations for the annotated block lists (>= 2^23)");
+        ctx->n_done = 0;
+        if (ctx->n_assigned == 0) { if (assign_round(ctx, nullptr, 0)) return 1; }     // device permutation
+        else if (ctx->n_assigned != 1) FAIL("hmy_init_from_centroids: more than one permutation queued");
+        CK(cudaMemsetAsync(ctx->zero_round, 0, (4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double), ctx->stream));   // obj | Ofresh | Yacc
+        CK(cudaMemsetAsync(ctx->t5_dnew, 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
+        CK(cudaMemsetAsync(ctx->t5_told[ctx->told_cur], 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
+        if (timer_begin(ctx, ctx->ev_init)) return 1;
+        if (launch_tc5(ctx, 1)) return 1;
+        if (timer_end(ctx, ctx->ev_init)) return 1;
+        ctx->rsum_cur ^= 1;
+        swap_centroids(ctx);
+        ctx->have_init = true;
+        return fetch_obj_tc5(ctx, obj);
+    }
+    ctx->t5_state = false; ctx->r_valid = true;
     CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));     // obj | Ofresh | Yacc | Told | Dnew
     if (timer_begin(ctx, ctx->ev_init)) return 1;
     if (ctx->persistent && (!ctx->ar || ctx->fused)) {
@@ -660,6 +777,36 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
     HmyDev& st = ctx->st;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_init) FAIL("hmy_kmeans_round: call hmy_init_from_centroids first");
+    if (use_tc5(ctx)) {
+        // one round ahead: perm_host (or the device permutation) is the NEXT round's; this round's was queued by the
+        // previous call (the first one by hmy_queue_perm / hmy_init_from_centroids)
+        if (!ctx->t5_state) FAIL("hmy_kmeans_round: the context switched kernels after init");
+        const long long r = ctx->n_done;
+        if (ctx->n_assigned == r + 1) { if (assign_round(ctx, perm_host, r + 1)) return 1; }
+        else if (ctx->n_assigned != r + 2 || perm_host) FAIL("hmy_kmeans_round: permutation queue out of step");
+        {
+            HmyDev s = st;
+            s.blk = ctx->blkbuf[r & 1]; s.blk_next = ctx->blkbuf[(r + 1) & 1];
+            const size_t sm = ((size_t)st.nblk * HMY_LIST_THREADS + st.nblk) * sizeof(unsigned int);
+            HmyDev c1 = s; c1.list2 = nullptr;
+            k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(c1, ctx->d_cnt, 1);
+            k_block_scan<<<1, 32 * std::min(32, st.nblk), 0, ctx->stream>>>(s, ctx->d_cnt, ctx->list_chunks);
+            k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(s, ctx->d_cnt, 0);
+            ctx->launches += 3;
+            CK(cudaGetLastError());
+        }
+        CK(cudaMemsetAsync(ctx->zero_round, 0, (4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double), ctx->stream));   // obj | Ofresh | Yacc
+        CK(cudaMemsetAsync(ctx->t5_dnew, 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
+        CK(cudaMemsetAsync(ctx->t5_told[ctx->told_cur ^ 1], 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
+        if (timer_begin(ctx, ctx->ev_round)) return 1;
+        if (launch_tc5(ctx, 0)) return 1;
+        if (timer_end(ctx, ctx->ev_round)) return 1;
+        ctx->told_cur ^= 1; ctx->rsum_cur ^= 1;
+        ctx->n_done++;
+        swap_centroids(ctx);
+        ctx->rounds++;
+        return fetch_obj_tc5(ctx, obj);
+    }
     // block of every cell for this round (harmony.py:471-475)
     if (perm_host) {
         if (!ctx->d_perm) CK(cudaMalloc((void**)&ctx->d_perm, (size_t)st.Nglobal * sizeof(long long)));
@@ -675,9 +822,10 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
     ctx->round_counter++;
     {   // per-block cell lists (stable counting sort over position chunks)
         const size_t sm = ((size_t)st.nblk * HMY_LIST_THREADS + st.nblk) * sizeof(unsigned int);
-        k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(st, ctx->d_cnt, 1);
-        k_block_scan<<<1, 32 * std::min(32, st.nblk), 0, ctx->stream>>>(st, ctx->d_cnt, ctx->list_chunks);
-        k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(st, ctx->d_cnt, 0);
+        HmyDev sl = st; sl.list2 = nullptr;            // plain position lists (the annotated ones belong to the tc5 path)
+        k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(sl, ctx->d_cnt, 1);
+        k_block_scan<<<1, 32 * std::min(32, st.nblk), 0, ctx->stream>>>(sl, ctx->d_cnt, ctx->list_chunks);
+        k_block_lists<<<ctx->list_chunks, HMY_LIST_THREADS, sm, ctx->stream>>>(sl, ctx->d_cnt, 0);
         ctx->launches += 3;
         CK(cudaGetLastError());
     }
@@ -715,6 +863,7 @@ extern "C" int hmy_ridge_correct(hmy_ctx* ctx) {
     HmyDev& st = ctx->st;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_init) FAIL("hmy_ridge_correct: call hmy_init_from_centroids first");
+    if (!ctx->r_valid) FAIL("hmy_ridge_correct: the last stage did not store R (option write_r = 0)");
     CK(cudaMemsetAsync(ctx->zero_ridge, 0, ctx->zero_ridge_bytes, ctx->stream));
     CK(cudaMemsetAsync(st.Yacc, 0, (size_t)st.K * st.dp * sizeof(double), ctx->stream));
     if (timer_begin(ctx, ctx->ev_ridge)) return 1;
@@ -746,6 +895,7 @@ extern "C" int hmy_ridge_correct(hmy_ctx* ctx) {
         void* args[] = {&s, &what, &mode};
         if (launch(ctx, (const void*)k_tables, dim3(1), dim3(HMY_THREADS), args, 0, false)) return 1;
     }
+    if (split_zcos(ctx)) return 1;           // the round kernel's operand rows follow the new Z_cos
     if (timer_end(ctx, ctx->ev_ridge)) return 1;
     ctx->ridge_passes++;
     return 0;
@@ -811,7 +961,9 @@ extern "C" int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes) {
         case HMY_Z_CORR: return get_cells(ctx, st.Zcorr, st.dp, st.d, host_out, bytes);
         case HMY_Z_COS: return get_cells(ctx, st.Zcos, st.dp, st.d, host_out, bytes);
         case HMY_Z_ORIG: return get_cells(ctx, st.Zorig, st.dp, st.d, host_out, bytes);
-        case HMY_R: return get_cells(ctx, st.R, st.Kp, st.K, host_out, bytes);
+        case HMY_R:
+            if (!ctx->r_valid) FAIL("hmy_get(R): the last stage did not store R (option write_r = 0)");
+            return get_cells(ctx, st.R, st.Kp, st.K, host_out, bytes);
         case HMY_Y: {
             if ((size_t)bytes != (size_t)st.K * st.d * sizeof(float)) FAIL("hmy_get(Y): wrong buffer size");
             std::vector<float> t((size_t)st.K * st.dp);
@@ -838,7 +990,7 @@ extern "C" int hmy_get(hmy_ctx* ctx, int which, void* host_out, int64_t bytes) {
             return 0;
         }
         case 9: {   // HMY_TRACE: uint64 [grid][HMY_TRACE_SLOTS] globaltimer stamps of the last round
-            const size_t n = (size_t)((ctx->use_tc5 ? ctx->G_tc5 : ctx->G) + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long);
+            const size_t n = (size_t)((use_tc5(ctx) ? ctx->G_tc5 : ctx->G) + 1) * HMY_TRACE_SLOTS * sizeof(unsigned long long);
             if (!st.trace) FAIL("hmy_get(trace): tracing is off");
             if ((size_t)bytes != n) FAIL("hmy_get(trace): wrong buffer size");
             CK(cudaStreamSynchronize(ctx->stream));
@@ -868,7 +1020,10 @@ extern "C" int hmy_synchronize(hmy_ctx* ctx) {
 extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
     const std::string n(name ? name : "");
     if (n == "persistent") { ctx->persistent = value != 0; return 0; }
-    if (n == "seed") { ctx->seed = (unsigned long long)value * 0x9E3779B97F4A7C15ull + 0x243F6A8885A308D3ull; ctx->round_counter = 0; return 0; }
+    if (n == "seed") {
+        if (ctx->n_assigned > 0) FAIL("option seed: a permutation of the current run is already queued (set the seed before init)");
+        ctx->seed = (unsigned long long)value * 0x9E3779B97F4A7C15ull + 0x243F6A8885A308D3ull; ctx->round_counter = 0; return 0;
+    }
     if (n == "timing") { ctx->timing = value != 0; return 0; }
     if (n == "trace") {
         // per-CTA timeline of the persistent round kernel (debug / profiling aid)
@@ -901,8 +1056,9 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
     }
     if (n == "tc5") {
         if (ctx->have_params) FAIL("option tc5 must be set before hmy_set_params");
-        ctx->want_tc5 = value != 0; return 0;
+        ctx->want_tc5 = (int)value; return 0;
     }
+    if (n == "write_r") { ctx->write_r = value != 0; return 0; }
     if (n == "reset") {
         // back to the freshly-uploaded state (benchmark steps restart from here)
         CK(cudaSetDevice(ctx->device));
@@ -911,7 +1067,10 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
         k_reset<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->st);
         ctx->launches++;
         CK(cudaGetLastError());
+        if (split_zcos(ctx)) return 1;
         ctx->have_init = false;
+        ctx->round_counter = 0; ctx->n_assigned = 0; ctx->n_done = 0;      // the permutation stream starts over as well
+        ctx->ycur = 0; ctx->st.Yhat = ctx->Ybuf[0]; ctx->st.Ynext = ctx->Ybuf[1]; ctx->Ylast = ctx->Ybuf[0];
         return 0;
     }
     FAIL("hmy_set_option: unknown option");
@@ -922,15 +1081,17 @@ extern "C" int64_t hmy_counter(const hmy_ctx* ctx, const char* name) {
     if (n == "launches") return ctx->launches;
     if (n == "rounds") return ctx->rounds;
     if (n == "ridge_passes") return ctx->ridge_passes;
-    if (n == "grid") return ctx->use_tc5 ? ctx->G_tc5 : ctx->G;
+    if (n == "grid") return use_tc5(ctx) ? ctx->G_tc5 : ctx->G;
     if (n == "fused") return ctx->fused ? 1 : 0;
-    if (n == "smem_round") return ctx->use_tc5 ? ctx->smem_tc5 : ctx->smem_round;
+    if (n == "smem_round") return use_tc5(ctx) ? ctx->smem_tc5 : ctx->smem_round;
     if (n == "nblk") return ctx->st.nblk;
     if (n == "ncombo") return ctx->st.ncombo;
     if (n == "mma") return ctx->use_mma ? 1 : 0;
     if (n == "ridge_mma") return ctx->ridge_mma ? 1 : 0;
-    if (n == "round_threads") return ctx->use_tc5 ? TC5_TILE : ctx->round_threads;
-    if (n == "tc5") return ctx->use_tc5 ? 1 : 0;
+    if (n == "round_threads") return use_tc5(ctx) ? T5_THREADS : ctx->round_threads;
+    if (n == "tc5") return use_tc5(ctx) ? 1 : 0;
+    if (n == "lookahead") return use_tc5(ctx) ? 1 : 0;      // 1: permutations are queued one round ahead (hmy_queue_perm)
+    if (n == "r_valid") return ctx->r_valid ? 1 : 0;
     return -1;
 }
 

@@ -68,6 +68,14 @@ struct HmyDev {
     unsigned int xseq_base;          // sequence number of the last exchange before this launch
     unsigned long long xslot;        // bytes of one payload slot (fenced protocol)
     int xll_count;                   // elements of one low-latency slot (K x B)
+    // ---- tensor-memory round kernel (hmy_round_tc5.cuh)
+    unsigned short* Zs16;            // [N][32 dt] fp16: hi[16 dt] | lo[16 dt] of 1024 * Z_cos, dt = ceil(d / 16)
+    int2* list2;                     // annotated block lists of the round: {cell, combo << 8 | block of the cell in the NEXT round}
+    unsigned char* blk_next;         // block of every cell in the next round
+    float* Told_next;                // [nblk][B][K] sums the NEXT round's blocks remove (accumulated by this round)
+    double* Rsum; double* Rsum_next; // [K] running sum_n R[n][k] of this round / start value of the next one
+    unsigned long long* bar64;       // monotone grid-barrier counter
+    int write_R;                     // 1: the round stores the new R rows to HBM
 };
 
 __device__ __forceinline__ void hmy_trace(const HmyDev& st, int slot) {

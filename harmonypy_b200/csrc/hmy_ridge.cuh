@@ -11,6 +11,7 @@
 // consecutive cells of ONE combination) turns the per-batch gathers of the reference into a
 // plain (K x n)(n x d) contraction over a contiguous range of HBM.
 #pragma once
+#include <cuda_fp16.h>
 #include "hmy_common.cuh"
 
 #define HMY_SEG_MAX 1024
@@ -354,6 +355,24 @@ __global__ void k_reset(HmyDev st) {
         st.Zcorr[(size_t)p * st.dp + j] = z;
         st.Zcos[(size_t)p * st.dp + j] = z / nrm;
     }
+}
+
+// Z_cos -> the pre-split operand rows of the tensor-memory round kernel (hmy_round_tc5.cuh): per cell
+// hi[16 dt] | lo[16 dt] halves of 1024 * z (zero padded), one thread per pair of PCs
+__global__ void k_split_zcos(HmyDev st) {
+    const int dt = (st.d + 15) >> 4, pairs = 8 * dt;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.N * pairs) return;
+    const long long p = i / pairs;
+    const int j2 = (int)(i - p * pairs), j = 2 * j2;
+    const float* z = st.Zcos + (size_t)p * st.dp;
+    const float x0 = (j < st.dp) ? z[j] * 1024.0f : 0.f, x1 = (j + 1 < st.dp) ? z[j + 1] * 1024.0f : 0.f;
+    const __half2 H = __floats2half2_rn(x0, x1);
+    const float2 hf = __half22float2(H);
+    const __half2 L = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+    unsigned int* row = reinterpret_cast<unsigned int*>(st.Zs16) + (size_t)p * (2 * pairs);
+    row[j2] = *reinterpret_cast<const unsigned int*>(&H);
+    row[pairs + j2] = *reinterpret_cast<const unsigned int*>(&L);
 }
 
 // dst[order[p]][0..w) = src[p][0..w)   (src row stride sp)

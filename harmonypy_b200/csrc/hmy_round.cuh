@@ -631,7 +631,8 @@ __global__ void __launch_bounds__(HMY_LIST_THREADS) k_block_lists(HmyDev st, int
     for (int i = t0; i < t1; ++i) {
         const int b = st.blk[c0 + i];
         const long long pos = st.blk_start[b] + cnt[(size_t)blockIdx.x * nblk + b] + s_cnt[b * HMY_LIST_THREADS + tid]++;
-        st.list[pos] = (int)(c0 + i);
+        if (st.list2 != nullptr) st.list2[pos] = make_int2((int)(c0 + i), (st.combo[c0 + i] << 8) | (int)st.blk_next[c0 + i]);
+        else st.list[pos] = (int)(c0 + i);
     }
 }
 

@@ -1,194 +1,791 @@
-// tcgen05 / tensor-memory version of the k-means round (opt-in: engine option "tc5").
+// The k-means round of Harmony (harmony.py:437-513) on tcgen05 / tensor memory, warp-specialised.
 //
-// STATUS: written at the end of round 1 after the GPU budget was used up.  Its inner loop -- the tile step
-// (1)-(3) below with exactly these layouts, descriptors and fences -- ran stand-alone on a B200
-// (experiments/tcgen05_tile_step_probe.cu: R 8e-7, sums 2-3e-6 against fp64), but THIS kernel, with the
-// block lists, tables and barriers around it, has not run yet: it is NOT selected by default and the parity
-// tests only run it when HMY_TEST_TC5=1.
+// One persistent cooperative launch per round, ONE CTA per SM, 18 warps:
 //
-// Same algorithm and the same grid-level structure as k_round_mma (hmy_round_mma.cuh): phase 0, the
-// per-CTA K x B tables, the block lists, the barriers and the multi-GPU communication CTA are reused
-// unchanged.  Only the per-block cell processing differs:
+//   warp 16  PRODUCER   walks the CTA's share of every block's annotated cell list (int2 {cell, combo << 8 | block
+//                       of the cell in the NEXT round}), builds 128-row tiles (a change of covariate combination
+//                       starts on a 16-row boundary, so every 16-cell K step of the accumulation has ONE combination)
+//                       and gathers the cells' Z_cos rows -- kept pre-split as fp16 hi | lo (hmy_common.cuh: Zs16) --
+//                       with 16-byte cp.async straight into the K-major core-matrix layout of a 3-stage ring.
+//   warp 17  MMA        one thread issues every tcgen05.mma:  scoring  D1[cell][cluster] = Z . Y^T  (fp16 two-way
+//                       split, fp32 accumulate, two D1 buffers) as soon as a stage has landed, and the accumulation
+//                       of a finished tile  D2y[cluster][PC] += R^T Z,  D2o[slot][cluster] += R^T 1,
+//                       D2t[slot][cluster][next block] += R^T onehot(next block)  in tensor memory.
+//   warps 0-15 EPILOGUE thread = (cell, quarter of the clusters): tcgen05.ld of the scores, exp2, penalty, the
+//                       softmax / normalisation sums (four threads per cell meet through shared memory), objective
+//                       terms in closed form (no log per entry), the new R as fp16 hi/lo into the MN-major operand
+//                       tile.  Between blocks: flush D2o into the running O (fp64 atomics), grid barrier, penalty
+//                       rows of the combinations this CTA meets (read from the running O: O(K) per CTA and block,
+//                       independent of B).
 //
-//   tile = 128 cells = the 128 lanes of tensor memory; CTA = 128 threads; THREAD = CELL.
-//   (1) scoring     D1[cell][cluster]  = Zs . Ys^T      tcgen05.mma kind::f16, M = 128, N = 16 NC, fp16
-//                   hi/lo split (3 MMAs per 16 PCs), operands in shared memory in the canonical no-swizzle
-//                   K-major layout, one thread issues, completion through tcgen05.commit -> mbarrier
-//   (2) epilogue    every thread reads ITS cell's scores with tcgen05.ld.32x32b: the softmax sums, the
-//                   penalty product, the objective terms are thread-local (no shuffles, no fragment
-//                   bookkeeping); the new R row goes to HBM and, as fp16 hi/lo, to shared memory in the
-//                   MN-major layout (harmony.py:466-468, :495-503)
-//   (3) sums        D2y[cluster][PC]    += R^T . Zs     (harmony.py:443; the Z tile of (1) read MN-major)
-//                   D2o[cluster][level] += R^T . onehot (harmony.py:506-507; multi-hot level rows)
-//                   accumulated IN TENSOR MEMORY: D2o over a block (then thread = cluster adds its row to
-//                   Dnew / Ofresh), D2y over the whole round (then thread = cluster adds its row to Yacc).
+// What is NOT done any more compared with k_round_mma (hmy_round_mma.cuh):
+//   * no phase 0: the sums a block removes from O before its update (harmony.py:491-492) are the sums of the
+//     assignments as of the END of the previous round grouped by THIS round's blocks; the previous round
+//     accumulated them in tensor memory (D2t) because it already knew this round's block of every cell
+//     (the host / the device permutation runs one round ahead) -- 400 B/cell of R re-reads gone;
+//   * R is not written to HBM unless the host asks (write_R): nothing on the device reads it between rounds;
+//     the host asks in the rounds after which cluster() can stop (harmony.py:455-458) because the ridge
+//     correction and the R property need it -- another 400 B/cell gone in the other rounds;
+//   * no K x B tables in shared memory and no O(B K) table update per CTA and block.
 //
-// Limits: K <= 128, d <= 64, B <= 32, nblk <= 32; everything else stays on k_round_mma.
+// Limits: K <= 128, d <= 64, <= 32 blocks, one GPU per launch domain (multi-GPU runs stay on k_round_mma).
 #pragma once
 #include "hmy_round_mma.cuh"
 
-#define TC5_TILE 128          // cells per tile
-#define TC5_DP 64             // PCs (padded)
-#define TC5_NB 32             // one-hot columns (padded)
-#define TC5_KM 128            // clusters as the M of the accumulation
-#define TC5_TMEM_COLS 256     // D1: [0, 16 NC)   D2y: [128, 192)   D2o: [192, 224)
-#define TC5_COL_Y 128
-#define TC5_COL_O 192
+#define T5_TILE 128
+#define T5_NZ 3
+#define T5_SLOTS 4
+#define T5_EPI_WARPS 16
+#define T5_EPI_THREADS (32 * T5_EPI_WARPS)
+#define T5_WARP_PROD 16
+#define T5_WARP_MMA 17
+#define T5_THREADS (32 * (T5_EPI_WARPS + 2))
+// tensor-memory columns (512 allocated)
+#define T5_COL_D1 0              // + 128 * buffer
+#define T5_COL_Y 256
+#define T5_COL_O 320             // + 16 * slot (every column of a slot holds the same sum)
+#define T5_COL_T 384             // + 32 * slot + next block
+// shared memory (dynamic, 1024-byte aligned)
+#define T5_SZ_ZPART 16384
+#define T5_SZ_STAGE 32768
+#define T5_SZ_RPART 32768
+#define T5_OFF_Z 0
+#define T5_OFF_RH (T5_NZ * T5_SZ_STAGE)
+#define T5_OFF_RL (T5_OFF_RH + T5_SZ_RPART)
+#define T5_OFF_NB (T5_OFF_RL + T5_SZ_RPART)          // one-hot(next block): 32 columns x 128 cells
+#define T5_OFF_ONES (T5_OFF_NB + 8192)                // 16 columns x 16 cells of 1.0
+#define T5_OFF_YH (T5_OFF_ONES + 512)
+__host__ __device__ constexpr int t5_off_yl(int NC) { return T5_OFF_YH + NC * 2048; }
+__host__ __device__ constexpr int t5_off_ps(int NC) { return t5_off_yl(NC) + NC * 2048; }      // float2 [4][KT2] {pen, sigma ln pen}
+__host__ __device__ constexpr int t5_off_ck(int NC) { return t5_off_ps(NC) + T5_SLOTS * 16 * NC * 8; }   // float2 [KT2] {-log2e / sigma, sigma}
+__host__ __device__ constexpr int t5_off_xch(int NC) { return t5_off_ck(NC) + 16 * NC * 8; }   // float2 [2][4][128]
+__host__ __device__ constexpr int t5_off_meta(int NC) { return t5_off_xch(NC) + 2 * 4 * 128 * 8; }
+__host__ __device__ constexpr int t5_off_bar(int NC) { return t5_off_meta(NC) + T5_NZ * 1024; }
+__host__ __device__ constexpr int t5_smem_bytes(int NC) { return t5_off_bar(NC) + 256; }
+// per-stage tile description written by the producer: int cell[128] | u16 slotnb[128] | header
+#define T5_META_SLOTNB 512
+#define T5_META_HDR 768
+#define T5_H_FLAGS 0
+#define T5_H_BLK 1
+#define T5_H_MASK 2              // slots used by this tile
+#define T5_H_COMBO 4             // [4] combination of every slot (-1: free)
+#define T5_H_KSLOT 8             // [2] slot of every 16-row K step, one byte each (0xFF: no cells)
+#define T5_H_LEV 12              // u16 [4][8] one-hot rows of every slot's combination (16-byte aligned)
+#define T5_F_EMPTY 1
+#define T5_F_LAST_BLOCK 2
+#define T5_F_LAST_ROUND 4
+#define T5_F_EVICT 8
+// mbarriers
+#define T5_B_ZFULL 0             // [3] producer -> MMA / epilogue
+#define T5_B_ACC 3               // [3] accumulation of the stage's tile done (tcgen05.commit)
+#define T5_B_SFULL 6             // [2] scores in D1[d]
+#define T5_B_SFREE 8             // [2] D1[d] read by every epilogue warp
+#define T5_B_RFULL 10            // operand tiles of the accumulation written
+#define T5_B_ODONE 11            // D2o of the block's last tile complete
 
-// canonical no-swizzle operand layouts (8 x 16-byte core matrices; CUTLASS make_umma_desc):
-// LBO = byte stride between core matrices along k, SBO = along m/n
-#define TC5_Z_LBO_K 128       // Z tile as K-major A of the scoring: (cell, PC)
-#define TC5_Z_SBO_K 1024
-#define TC5_Z_LBO_MN 1024     // the same bytes as MN-major B of the accumulation: (PC, cell)
-#define TC5_Z_SBO_MN 128
-#define TC5_Y_LBO 128         // centroids, K-major B of the scoring: (cluster, PC)
-#define TC5_Y_SBO 1024
-#define TC5_R_LBO 128         // R tile, MN-major A of the accumulation: (cluster, cell), cluster blocks outermost
-#define TC5_R_SBO 2048
-#define TC5_O_LBO 128         // one-hot tile, MN-major B: (level, cell)
-#define TC5_O_SBO 2048
+// canonical no-swizzle layouts (8 rows x 16 bytes core matrices)
+#define T5_LBO_K 128             // K-major: next 8-wide k chunk
+#define T5_SBO_K 1024            //          next 8 rows
+#define T5_Z_LBO_MN 1024         // the Z tile read MN-major (PC, cell): next 8 cells
+#define T5_Z_SBO_MN 128          //                                      next 8 PCs
+#define T5_R_LBO 128             // MN-major (cluster, cell): next 8 cells
+#define T5_R_SBO 2048            //                           next 8 clusters
 
-#define TC5_OFF_ZH 0
-#define TC5_OFF_ZL (TC5_OFF_ZH + TC5_TILE * TC5_DP * 2)
-#define TC5_OFF_RH (TC5_OFF_ZL + TC5_TILE * TC5_DP * 2)
-#define TC5_OFF_RL (TC5_OFF_RH + TC5_KM * TC5_TILE * 2)
-#define TC5_OFF_OT (TC5_OFF_RL + TC5_KM * TC5_TILE * 2)
-#define TC5_OFF_YH (TC5_OFF_OT + TC5_NB * TC5_TILE * 2)
-__host__ __device__ constexpr int tc5_off_yl(int NC) { return TC5_OFF_YH + 16 * NC * TC5_DP * 2; }
-__host__ __device__ constexpr int tc5_off_c1(int NC) { return tc5_off_yl(NC) + 16 * NC * TC5_DP * 2; }
-__host__ __device__ constexpr int tc5_off_c3(int NC) { return tc5_off_c1(NC) + 16 * NC * 4; }
-__host__ __device__ constexpr int tc5_off_ps(int NC) { return tc5_off_c3(NC) + 16 * NC * 4; }
-
-struct Tc5Smem {
-    int KT2, RSH;
-    int off_Zh, off_Zl, off_Rh, off_Rl, off_Ot, off_Yh, off_Yl, off_c1, off_c3, off_Ps, off_Os, off_prb, off_cell, off_misc;
-    int total;
-};
-
-__host__ __device__ inline Tc5Smem tc5_smem_plan(int B, int NC) {
-    Tc5Smem s;
-    s.KT2 = 16 * NC;
-    s.RSH = hmy_odd8(s.KT2);                       // row stride of the phase-0 R tile (aliases the R tiles below)
-    // everything up to the penalty table sits at an offset that only depends on NC: the kernel addresses it
-    // relative to ONE base register (TC5_OFF_* below)
-    int o = 0;
-    s.off_Zh = TC5_OFF_ZH; s.off_Zl = TC5_OFF_ZL; s.off_Rh = TC5_OFF_RH; s.off_Rl = TC5_OFF_RL; s.off_Ot = TC5_OFF_OT;
-    s.off_Yh = TC5_OFF_YH;
-    s.off_Yl = tc5_off_yl(NC); s.off_c1 = tc5_off_c1(NC); s.off_c3 = tc5_off_c3(NC); s.off_Ps = tc5_off_ps(NC);
-    o = s.off_Ps + B * s.KT2 * 4;
-    s.off_Os = o; o += B * s.KT2 * 4;
-    s.off_prb = o; o += 2 * B * 4;
-    o = (o + 15) & ~15;
-    s.off_cell = o; o += TC5_TILE * 4;
-    o = (o + 15) & ~15;
-    s.off_misc = o; o += 8 * 256 + 128;
-    s.total = o;
-    return s;
-}
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long tc5_desc(unsigned int saddr, unsigned int lbo, unsigned int sbo) {
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long t5_desc(unsigned int saddr, unsigned int lbo, unsigned int sbo) {
     unsigned long long d = 0;
-    d |= (unsigned long long)((saddr >> 4) & 0x3FFFu);              // start address        [0,14)
-    d |= (unsigned long long)((lbo >> 4) & 0x3FFFu) << 16;          // leading byte offset  [16,30)
-    d |= (unsigned long long)((sbo >> 4) & 0x3FFFu) << 32;          // stride byte offset   [32,46)
-    d |= 1ull << 46;                                                // version 1; layout_type 0 = no swizzle
+    d |= (unsigned long long)((saddr >> 4) & 0x3FFFu);
+    d |= (unsigned long long)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (unsigned long long)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
     return d;
 }
-__device__ __forceinline__ unsigned int tc5_idesc(int m, int n, int a_mn_major, int b_mn_major) {
-    unsigned int d = 0;
-    d |= 1u << 4;                                                   // D = f32; A, B = f16
-    d |= (unsigned int)a_mn_major << 15;
-    d |= (unsigned int)b_mn_major << 16;
-    d |= (unsigned int)(n >> 3) << 17;
-    d |= (unsigned int)(m >> 4) << 24;
-    return d;
+__device__ __forceinline__ unsigned int t5_idesc(int m, int n, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((unsigned int)a_mn_major << 15) | ((unsigned int)b_mn_major << 16) | ((unsigned int)(n >> 3) << 17) | ((unsigned int)(m >> 4) << 24);
 }
-__device__ __forceinline__ void tc5_mma(unsigned int tmem, unsigned long long da, unsigned long long db, unsigned int idesc, unsigned int accumulate) {
+__device__ __forceinline__ void t5_mma(unsigned int tmem, unsigned long long da, unsigned long long db, unsigned int idesc, unsigned int accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc5_commit(unsigned long long* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void t5_commit(unsigned int bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// An MMA that never completes (bad descriptor, lost commit) must become an error, not a hung cooperative
-// grid: after ~2 s of waiting the kernel traps and the host sees a launch failure.
-__device__ __forceinline__ void tc5_wait(unsigned long long* bar, unsigned int parity) {
-    unsigned int done = 0, spins = 0;
+__device__ __forceinline__ void t5_arrive(unsigned int bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool t5_test(unsigned int bar, unsigned int parity) {
+    unsigned int done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
+}
+// A completion that never comes (bad descriptor, lost arrival) must become an error, not a hung cooperative grid
+__device__ __forceinline__ void t5_wait(unsigned int bar, unsigned int parity) {
+    unsigned int spins = 0;
     unsigned long long t0 = 0;
-    while (!done) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (!done && (++spins & 1023u) == 0u) {
+    while (!t5_test(bar, parity)) {
+        if ((++spins & 255u) == 0u) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             if (t0 == 0) t0 = t;
-            else if (t - t0 > 2000000000ull) __trap();
+            else if (t - t0 > 4000000000ull) __trap();
         }
     }
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-__device__ __forceinline__ void tc5_ld16(unsigned int taddr, float (&v)[16]) {
+__device__ __forceinline__ void t5_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t5_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void t5_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void t5_ld16(unsigned int taddr, float* v) {
     unsigned int u[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
         : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
           "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(u[j]);
 }
-// generic-proxy shared-memory writes -> async proxy (the MMA reads shared memory through it), the CTA's
-// tensor-memory loads -> before the next MMA, then the hand-off to the issuing thread
-__device__ __forceinline__ void tc5_publish() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+__device__ __forceinline__ void t5_ld8(unsigned int taddr, float* v) {
+    unsigned int u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]) : "r"(taddr));
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(u[j]);
+}
+__device__ __forceinline__ float t5_ld1(unsigned int taddr) {
+    unsigned int u;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(u) : "r"(taddr));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void t5_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void t5_cp16(unsigned int dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void t5_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ---- per-CTA context ---------------------------------------------------------------------------------
-template <int NC>
-struct Tc5Ctx {
-    unsigned char* base;                 // dynamic shared memory; tiles / centroids / constants at TC5_OFF_*
-    int* sCell;
-    unsigned long long* bar;             // [0] scoring done, [1] accumulation done
-    unsigned int tmem, lane_base;
-    unsigned int ph_score, ph_acc;       // phases consumed so far (parity = & 1); identical in all threads
-    bool acc_pending;                    // an accumulation is in flight: it still reads the Z / R / one-hot tiles
-    bool y_started, o_started;           // D2y / D2o hold sums (first MMA into an empty accumulator overwrites)
-    int dt;                              // k-steps over the PCs
-    unsigned int mg_dp4;
-    __device__ __forceinline__ unsigned char* Zh() const { return base + TC5_OFF_ZH; }
-    __device__ __forceinline__ unsigned char* Zl() const { return base + TC5_OFF_ZL; }
-    __device__ __forceinline__ unsigned char* Rh() const { return base + TC5_OFF_RH; }
-    __device__ __forceinline__ unsigned char* Rl() const { return base + TC5_OFF_RL; }
-    __device__ __forceinline__ unsigned char* Ot() const { return base + TC5_OFF_OT; }
-    __device__ __forceinline__ unsigned char* Yh() const { return base + TC5_OFF_YH; }
-    __device__ __forceinline__ unsigned char* Yl() const { return base + tc5_off_yl(NC); }
-    __device__ __forceinline__ float* c1() const { return reinterpret_cast<float*>(base + tc5_off_c1(NC)); }
-    __device__ __forceinline__ float* c3() const { return reinterpret_cast<float*>(base + tc5_off_c3(NC)); }
-    __device__ __forceinline__ float* Ps() const { return reinterpret_cast<float*>(base + tc5_off_ps(NC)); }
-    // the staged tile, thread = cell
-    int cell; bool valid;
-    int lev[HMY_MAX_V];
-    double objd, obje;
-};
+// first cluster / number of 8-cluster groups of epilogue quarter q (the 16 NC columns split in whole groups of 8)
+template <int NC> __device__ __forceinline__ int t5_g0(int q) { return (NC == 7) ? ((q < 2) ? 4 * q : 8 + 3 * (q - 2)) : (NC / 2) * q; }
+template <int NC> __device__ __forceinline__ int t5_ng(int q) { return (NC == 7) ? ((q < 2) ? 4 : 3) : NC / 2; }
 
+// ---- producer warp ----------------------------------------------------------------------------------------------
+// Tile t of this CTA lives in stage t % 3.  Rows are filled from the block's share of the list; a new combination
+// starts on a 16-row boundary; a combination without a slot when all four are taken closes the tile (the next one
+// starts with an eviction: the epilogue flushes the per-slot accumulators before it goes on).
 template <int NC>
-__device__ __forceinline__ void tc5_wait_acc(Tc5Ctx<NC>& c) {
-    if (c.acc_pending) { tc5_wait(&c.bar[1], c.ph_acc & 1u); c.ph_acc++; c.acc_pending = false; }
+__device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, unsigned int bar0, unsigned int G) {
+    const int lane = threadIdx.x & 31;
+    const int dt = (st.d + 15) >> 4;
+    const size_t zrow = (size_t)64 * dt;                       // bytes of one Zs16 row: hi[16 dt] | lo[16 dt] halves
+    const unsigned char* Zs = reinterpret_cast<const unsigned char*>(st.Zs16);
+    int sc0 = -1, sc1 = -1, sc2 = -1, sc3 = -1, nslots = 0;   // slot table (warp-uniform)
+    unsigned short mylev = 0;                                  // lane = 8 slot + covariate: one-hot row of that slot's combination
+    unsigned int t = 0;
+    bool pending = false;                                      // tile t-1's copies are in flight, its zfull not yet signalled
+    const int nblocks = (mode == 1) ? 1 : st.nblk;
+    const unsigned int sbase = smem_u32(smem);
+    for (int blk = 0; blk < nblocks; ++blk) {
+        long long lb, le;
+        if (mode == 1) { lb = (long long)blockIdx.x * st.N / G; le = (long long)(blockIdx.x + 1) * st.N / G; }
+        else block_share(st, blk, blockIdx.x, G, lb, le);
+        long long cur = lb;
+        do {
+            const unsigned int s = t % T5_NZ, use = t / T5_NZ;
+            const unsigned int bacc = bar0 + 8u * (T5_B_ACC + s);
+            if (!t5_test(bacc, (use & 1u) ^ 1u)) {
+                // the stage is still in use: hand over the previous tile first, then wait
+                if (pending) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    t5_fence_async();
+                    __syncwarp();
+                    if (lane == 0) t5_arrive(bar0 + 8u * (T5_B_ZFULL + (t - 1u) % T5_NZ));
+                    pending = false;
+                }
+                t5_wait(bacc, (use & 1u) ^ 1u);
+            }
+            unsigned char* meta = smem + t5_off_meta(NC) + s * 1024;
+            int* mcell = reinterpret_cast<int*>(meta);
+            unsigned short* mslot = reinterpret_cast<unsigned short*>(meta + T5_META_SLOTNB);
+            int* hdr = reinterpret_cast<int*>(meta + T5_META_HDR);
+            // ---- candidate entries: i = lane + 32 j
+            const int navail = (int)min((long long)T5_TILE, le - cur);
+            int ecell[4], ecombo[4], enb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = lane + 32 * j;
+                ecell[j] = 0; ecombo[j] = -1; enb[j] = 0;
+                if (i < navail) {
+                    if (mode == 1) {
+                        const long long pos = cur + i;
+                        ecell[j] = (int)pos; ecombo[j] = st.combo[pos]; enb[j] = st.blk_next[pos];
+                    } else {
+                        const int2 e = __ldg(&st.list2[cur + i]);
+                        ecell[j] = e.x; ecombo[j] = e.y >> 8; enb[j] = e.y & 255;
+                    }
+                }
+                mslot[i] = 0xFFFFu; mcell[i] = 0;
+            }
+            __syncwarp();
+            int consumed = 0, row_base = 0, nrows = 0;
+            unsigned int flags = 0u, mask = 0u;
+            unsigned int ks_lo = 0xFFFFFFFFu, ks_hi = 0xFFFFFFFFu;
+            bool evicted = false;
+            while (consumed < navail && row_base < T5_TILE) {
+                const int jj = consumed >> 5;
+                const int mine_c = (jj == 0) ? ecombo[0] : (jj == 1) ? ecombo[1] : (jj == 2) ? ecombo[2] : ecombo[3];
+                const int c = __shfl_sync(0xffffffffu, mine_c, consumed & 31);
+                int mine = navail;
+#pragma unroll
+                for (int j = 3; j >= 0; --j) { const int i = lane + 32 * j; if (i >= consumed && i < navail && ecombo[j] != c) mine = i; }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+                const int run_end = mine;
+                int slot = (c == sc0) ? 0 : (c == sc1) ? 1 : (c == sc2) ? 2 : (c == sc3) ? 3 : -1;
+                if (slot < 0) {
+                    if (nslots == T5_SLOTS) {
+                        if (row_base != 0 || evicted) break;                 // close the tile; the next one evicts
+                        evicted = true; flags |= T5_F_EVICT;
+                        sc0 = sc1 = sc2 = sc3 = -1; nslots = 0;
+                    }
+                    slot = nslots++;
+                    if (slot == 0) sc0 = c; else if (slot == 1) sc1 = c; else if (slot == 2) sc2 = c; else sc3 = c;
+                    // the combination's one-hot rows travel with every tile (the epilogue derives penalties from them)
+                    if ((lane >> 3) == slot) mylev = (unsigned short)(((lane & 7) < st.V) ? st.combo_lev[c * st.V + (lane & 7)] : 0);
+                }
+                const int take = min(run_end - consumed, T5_TILE - row_base);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int i = lane + 32 * j;
+                    if (i >= consumed && i < consumed + take) {
+                        const int row = row_base + (i - consumed);
+                        mcell[row] = ecell[j];
+                        mslot[row] = (unsigned short)((slot << 8) | enb[j]);
+                    }
+                }
+                for (int ks = row_base >> 4; ks <= (row_base + take - 1) >> 4; ++ks) {
+                    if (ks < 4) ks_lo = (ks_lo & ~(0xFFu << (8 * ks))) | ((unsigned int)slot << (8 * ks));
+                    else ks_hi = (ks_hi & ~(0xFFu << (8 * (ks - 4)))) | ((unsigned int)slot << (8 * (ks - 4)));
+                }
+                mask |= 1u << slot;
+                consumed += take;
+                nrows = row_base + take;
+                row_base = (nrows + 15) & ~15;
+            }
+            cur += consumed;
+            if (consumed == 0 && navail > 0) { /* cannot happen: an eviction always frees a slot */ }
+            if (nrows == 0) flags |= T5_F_EMPTY;
+            if (cur >= le) flags |= T5_F_LAST_BLOCK | ((blk + 1 == nblocks) ? T5_F_LAST_ROUND : 0u);
+            reinterpret_cast<unsigned short*>(hdr + T5_H_LEV)[lane] = mylev;
+            __syncwarp();
+            if (lane == 0) {
+                hdr[T5_H_FLAGS] = (int)flags; hdr[T5_H_BLK] = blk; hdr[T5_H_MASK] = (int)mask;
+                hdr[T5_H_COMBO + 0] = sc0; hdr[T5_H_COMBO + 1] = sc1; hdr[T5_H_COMBO + 2] = sc2; hdr[T5_H_COMBO + 3] = sc3;
+                hdr[T5_H_KSLOT] = (int)ks_lo; hdr[T5_H_KSLOT + 1] = (int)ks_hi;
+            }
+            __syncwarp();
+            // ---- gather: 8 rows x 4 chunks of 16 bytes per instruction (conflict-free core-matrix writes)
+            {
+                const int r8 = lane & 7, cs = lane >> 3;
+                const unsigned int zs = sbase + T5_OFF_Z + s * T5_SZ_STAGE;
+                const int ngroups = (nrows + 7) >> 3;
+                for (int g = 0; g < ngroups; ++g) {
+                    const int row = 8 * g + r8;
+                    const bool valid = mslot[row] != 0xFFFFu;
+                    const unsigned char* src = Zs + (size_t)mcell[row] * zrow;
+                    const unsigned int drow = zs + (unsigned int)g * T5_SBO_K + (unsigned int)r8 * 16u;
+                    for (int cq = 0; cq < dt; ++cq) {
+                        const int ch = 4 * cq + cs;                    // chunk of the row: [0, 2 dt) hi, [2 dt, 4 dt) lo
+                        const int part = (ch >= 2 * dt) ? 1 : 0, cc = ch - part * 2 * dt;
+                        if (valid) t5_cp16(drow + (unsigned int)part * T5_SZ_ZPART + (unsigned int)cc * T5_LBO_K, src + ch * 16);
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            if (pending) {
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                t5_fence_async();
+                __syncwarp();
+                if (lane == 0) t5_arrive(bar0 + 8u * (T5_B_ZFULL + (t - 1u) % T5_NZ));
+            }
+            pending = true;
+            ++t;
+        } while (cur < le);
+    }
+    if (pending) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        t5_fence_async();
+        __syncwarp();
+        if (lane == 0) t5_arrive(bar0 + 8u * (T5_B_ZFULL + (t - 1u) % T5_NZ));
+    }
 }
 
-// centroids as fp16 hi/lo in the canonical K-major layout, per-cluster constants, empty tables
+// ---- MMA warp (one thread) -------------------------------------------------------------------------------------------
 template <int NC>
-__device__ void tc5_load_round_constants(Tc5Ctx<NC>& c, const HmyDev& st, float* Os, float* sPrb, float* sTheta) {
+__device__ void t5_mma_thread(const HmyDev& st, unsigned char* smem, unsigned int bar0, unsigned int tmem) {
+    const int dt = (st.d + 15) >> 4;
+    const unsigned int sb = smem_u32(smem);
+    const unsigned int id_score = t5_idesc(T5_TILE, 16 * NC, 0, 0), id_y = t5_idesc(128, 16 * dt, 1, 1);
+    const unsigned int id_o = t5_idesc(128, 16, 1, 1), id_t = t5_idesc(128, 32, 1, 1);
+    const unsigned long long dYh = t5_desc(sb + T5_OFF_YH, T5_LBO_K, T5_SBO_K), dYl = t5_desc(sb + t5_off_yl(NC), T5_LBO_K, T5_SBO_K);
+    const unsigned long long dRh = t5_desc(sb + T5_OFF_RH, T5_R_LBO, T5_R_SBO), dRl = t5_desc(sb + T5_OFF_RL, T5_R_LBO, T5_R_SBO);
+    const unsigned long long dOnes = t5_desc(sb + T5_OFF_ONES, 128, 256);
+    const unsigned long long dNb = t5_desc(sb + T5_OFF_NB, T5_R_LBO, T5_R_SBO);
+    unsigned int ts = 0, ta = 0;                       // next tile to score / to accumulate
+    bool score_end = false, y_started = false;
+    unsigned int o_started = 0u, t_started = 0u;       // per-slot: accumulator holds sums
+    unsigned int idle = 0; unsigned long long idle_t0 = 0;
+    for (;;) {
+        bool progressed = false;
+        if (!score_end) {
+            const unsigned int s = ts % T5_NZ, d = ts & 1u;
+            if (t5_test(bar0 + 8u * (T5_B_ZFULL + s), (ts / T5_NZ) & 1u) && t5_test(bar0 + 8u * (T5_B_SFREE + d), ((ts >> 1) & 1u) ^ 1u)) {
+                t5_fence_after();
+                const int* hdr = reinterpret_cast<const int*>(smem + t5_off_meta(NC) + s * 1024 + T5_META_HDR);
+                const unsigned int flags = (unsigned int)hdr[T5_H_FLAGS];
+                if (!(flags & T5_F_EMPTY)) {
+                    const unsigned int zh = sb + T5_OFF_Z + s * T5_SZ_STAGE, zl = zh + T5_SZ_ZPART;
+                    const unsigned long long dZh = t5_desc(zh, T5_LBO_K, T5_SBO_K), dZl = t5_desc(zl, T5_LBO_K, T5_SBO_K);
+                    for (int ks = 0; ks < dt; ++ks) {
+                        const unsigned long long o = (unsigned long long)((ks * 2 * T5_LBO_K) >> 4);
+                        t5_mma(tmem + T5_COL_D1 + 128u * d, dZl + o, dYh + o, id_score, ks > 0 ? 1u : 0u);
+                        t5_mma(tmem + T5_COL_D1 + 128u * d, dZh + o, dYl + o, id_score, 1u);
+                        t5_mma(tmem + T5_COL_D1 + 128u * d, dZh + o, dYh + o, id_score, 1u);
+                    }
+                }
+                t5_commit(bar0 + 8u * (T5_B_SFULL + d));
+                if (flags & T5_F_LAST_ROUND) score_end = true;
+                ++ts;
+                progressed = true;
+            }
+        }
+        if (ta < ts && t5_test(bar0 + 8u * T5_B_RFULL, ta & 1u)) {
+            t5_fence_after();
+            const unsigned int s = ta % T5_NZ;
+            const int* hdr = reinterpret_cast<const int*>(smem + t5_off_meta(NC) + s * 1024 + T5_META_HDR);
+            const unsigned int flags = (unsigned int)hdr[T5_H_FLAGS];
+            if (flags & T5_F_EVICT) { o_started = 0u; t_started = 0u; }
+            if (!(flags & T5_F_EMPTY)) {
+                const unsigned int kslo = (unsigned int)hdr[T5_H_KSLOT], kshi = (unsigned int)hdr[T5_H_KSLOT + 1];
+                const unsigned int zh = sb + T5_OFF_Z + s * T5_SZ_STAGE, zl = zh + T5_SZ_ZPART;
+                const unsigned long long dZh = t5_desc(zh, T5_Z_LBO_MN, T5_Z_SBO_MN), dZl = t5_desc(zl, T5_Z_LBO_MN, T5_Z_SBO_MN);
+                // the per-slot column sums first: they are what the end of a block waits for
+                for (int ks = 0; ks < 8; ++ks) {
+                    const unsigned int slot = ((ks < 4 ? kslo >> (8 * ks) : kshi >> (8 * (ks - 4))) & 0xFFu);
+                    if (slot == 0xFFu) continue;
+                    const unsigned long long ro = (unsigned long long)((ks * 2 * T5_R_LBO) >> 4);
+                    t5_mma(tmem + T5_COL_O + 16u * slot, dRh + ro, dOnes, id_o, (o_started >> slot) & 1u);
+                    t5_mma(tmem + T5_COL_O + 16u * slot, dRl + ro, dOnes, id_o, 1u);
+                    o_started |= 1u << slot;
+                }
+            }
+            if (flags & T5_F_LAST_BLOCK) t5_commit(bar0 + 8u * T5_B_ODONE);
+            if (!(flags & T5_F_EMPTY)) {
+                const unsigned int kslo = (unsigned int)hdr[T5_H_KSLOT], kshi = (unsigned int)hdr[T5_H_KSLOT + 1];
+                const unsigned int zh = sb + T5_OFF_Z + s * T5_SZ_STAGE, zl = zh + T5_SZ_ZPART;
+                const unsigned long long dZh = t5_desc(zh, T5_Z_LBO_MN, T5_Z_SBO_MN), dZl = t5_desc(zl, T5_Z_LBO_MN, T5_Z_SBO_MN);
+                for (int ks = 0; ks < 8; ++ks) {
+                    const unsigned int slot = ((ks < 4 ? kslo >> (8 * ks) : kshi >> (8 * (ks - 4))) & 0xFFu);
+                    if (slot == 0xFFu) continue;
+                    const unsigned long long ro = (unsigned long long)((ks * 2 * T5_R_LBO) >> 4);
+                    const unsigned long long zo = (unsigned long long)((ks * 2 * T5_Z_LBO_MN) >> 4);
+                    t5_mma(tmem + T5_COL_Y, dRl + ro, dZh + zo, id_y, y_started ? 1u : 0u);
+                    t5_mma(tmem + T5_COL_Y, dRh + ro, dZl + zo, id_y, 1u);
+                    t5_mma(tmem + T5_COL_Y, dRh + ro, dZh + zo, id_y, 1u);
+                    y_started = true;
+                    t5_mma(tmem + T5_COL_T + 32u * slot, dRh + ro, dNb + ro, id_t, (t_started >> slot) & 1u);
+                    t5_mma(tmem + T5_COL_T + 32u * slot, dRl + ro, dNb + ro, id_t, 1u);
+                    t_started |= 1u << slot;
+                }
+            }
+            t5_commit(bar0 + 8u * (T5_B_ACC + s));
+            if (flags & T5_F_LAST_BLOCK) o_started = 0u;
+            ++ta;
+            progressed = true;
+            if (flags & T5_F_LAST_ROUND) break;
+        }
+        if (progressed) { idle = 0; idle_t0 = 0; }
+        else if ((++idle & 255u) == 0u) {                 // nothing to issue for seconds: an error, not a hang
+            unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
+            if (idle_t0 == 0) idle_t0 = tn; else if (tn - idle_t0 > 4000000000ull) __trap();
+        }
+    }
+}
+
+// ---- epilogue warps ---------------------------------------------------------------------------------------------------
+// one-hot rows of slot q's combination: 8 x u16 held in registers by every thread of quarter q (the tile header
+// that carried them may be recycled by the producer before a flush reads them)
+struct T5Lev { uint4 w; __device__ __forceinline__ int get(int v) const { const unsigned int x = (v < 2) ? w.x : (v < 4) ? w.y : (v < 6) ? w.z : w.w; return (int)((v & 1) ? (x >> 16) : (x & 0xFFFFu)); } };
+
+// The O row of a (slot, cluster) pair as block `blk` sees it (harmony.py:491-492, :506-507): O of the previous stage
+// plus what the finished blocks put back (Dnew[i], complete once barrier i + 1 has been passed and never touched again)
+// minus what the blocks up to blk took out (Told[i], accumulated by the previous launch).  Every thread of quarter q
+// keeps the rows of slot q's levels (and the cluster's row sum) as running values; `upto` is the block they are at.
+struct T5Run { float o[HMY_MAX_V]; float rs; int upto; };
+
+// penalty rows {pen, sigma ln pen} of the slots in `need` (harmony.py:495-499); all 512 threads, quarter q = slot q,
+// thread-in-quarter = cluster
+template <int NC>
+__device__ void t5_penalty_rows(const HmyDev& st, int mode, unsigned char* smem, const T5Lev& lev, T5Run& run,
+                                unsigned int need, unsigned int live, int blk) {
     constexpr int KT2 = 16 * NC;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < KT2 * (TC5_DP / 2); i += TC5_TILE) {
-        const int k = i / (TC5_DP / 2), j = 2 * (i - k * (TC5_DP / 2));
+    const int tid = threadIdx.x, j = tid >> 7, k = tid & 127;
+    if (((need >> j) & 1u) && k < KT2) {
+        float2 out = make_float2(0.f, 0.f);
+        if (k < st.K) {
+            if (mode == 1) out = make_float2(1.f, 0.f);
+            else {
+                const size_t nBK = (size_t)st.B * st.K, nT = (size_t)st.nblk * nBK;
+                const float* ToldR = st.Told + nT; const float* DnewR = st.Dnew + nT;
+                if (!((live >> j) & 1u)) {
+                    // a slot this CTA has not met in this round: start from the previous stage's O
+#pragma unroll
+                    for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] = (v < st.V) ? (float)__ldcg(&st.O[(size_t)lev.get(v) * st.K + k]) : 0.f;
+                    run.rs = (float)__ldcg(&st.Rsum[k]);
+                    run.upto = -1;
+                }
+                while (run.upto < blk) {
+                    const int i = ++run.upto;
+                    float a[HMY_MAX_V], r[HMY_MAX_V];
+#pragma unroll
+                    for (int v = 0; v < HMY_MAX_V; ++v) {
+                        const size_t e = (size_t)lev.get(v) * st.K + k;
+                        a[v] = (v < st.V && i > 0) ? __ldcg(&st.Dnew[(size_t)(i - 1) * nBK + e]) : 0.f;
+                        r[v] = (v < st.V) ? __ldcg(&st.Told[(size_t)i * nBK + e]) : 0.f;
+                    }
+                    const float ar = (i > 0) ? __ldcg(&DnewR[(size_t)(i - 1) * st.K + k]) : 0.f, rr = __ldcg(&ToldR[(size_t)i * st.K + k]);
+#pragma unroll
+                    for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] += a[v] - r[v];
+                    run.rs += ar - rr;
+                }
+                float pen = 0.f;
+#pragma unroll
+                for (int v = 0; v < HMY_MAX_V; ++v)
+                    if (v < st.V) {
+                        const int b = lev.get(v);
+                        const float e = run.rs * __ldg(&st.Pr_b[b]);
+                        const float ratio = fminf(fmaxf(e / fmaxf(run.o[v] + e, 1e-8f), 1e-8f), 1.0f);
+                        const float th = __ldg(&st.theta[b]);
+                        pen += (th == 2.0f) ? ratio * ratio : powf(ratio, th);
+                    }
+                out.x = pen;
+                out.y = (pen > 0.f) ? __ldg(&st.sigma[k]) * logf(pen) : 0.f;
+            }
+        }
+        reinterpret_cast<float2*>(smem + t5_off_ps(NC))[j * KT2 + k] = out;
+    }
+    t5_bar_sync(1, T5_EPI_THREADS);
+}
+
+// per-slot column sums of the finished tiles of this block -> the block's re-added sums (harmony.py:506-507)
+__device__ __forceinline__ void t5_flush_o(const HmyDev& st, unsigned int tmem, const T5Lev& lev, unsigned int mask, int blk) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp >> 2, k = 32 * (warp & 3) + lane;
+    if ((mask >> q) & 1u) {                                  // warps of quarter q take slot q (lane = cluster)
+        const float v = t5_ld1(tmem + ((unsigned int)(32 * (warp & 3)) << 16) + T5_COL_O + 16u * q);
+        t5_ld_wait();
+        const float x = v * (1.0f / HMY_OPSCALE);
+        if (k < st.K && x != 0.f) {
+            const size_t nBK = (size_t)st.B * st.K;
+            float* dn = st.Dnew + (size_t)blk * nBK;
+            for (int vv = 0; vv < st.V; ++vv) atomicAdd(&dn[(size_t)lev.get(vv) * st.K + k], x);
+            atomicAdd(&st.Dnew[(size_t)st.nblk * nBK + (size_t)blk * st.K + k], x);          // row sums (every cell has one level of covariate 0)
+        }
+    }
+}
+// per-slot sums by NEXT round's block -> the table that round removes block by block (harmony.py:491-492)
+__device__ __forceinline__ void t5_flush_t(const HmyDev& st, unsigned int tmem, const T5Lev& lev, unsigned int mask) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp >> 2, k = 32 * (warp & 3) + lane;
+    if ((mask >> q) & 1u) {
+        float v[32];
+        const unsigned int ta = tmem + ((unsigned int)(32 * (warp & 3)) << 16) + T5_COL_T + 32u * q;
+        t5_ld16(ta, v); t5_ld16(ta + 16u, v + 16);
+        t5_ld_wait();
+        if (k < st.K) {
+#pragma unroll
+            for (int nb = 0; nb < 32; ++nb) {
+                const float x = v[nb] * (1.0f / HMY_OPSCALE);
+                if (nb < st.nblk && x != 0.f) {
+                    for (int vv = 0; vv < st.V; ++vv) atomicAdd(&st.Told_next[((size_t)nb * st.B + lev.get(vv)) * st.K + k], x);
+                    atomicAdd(&st.Told_next[(size_t)st.nblk * st.B * st.K + (size_t)nb * st.K + k], x);
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void t5_grid_barrier(const HmyDev& st, unsigned long long target) {
+    t5_bar_sync(1, T5_EPI_THREADS);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        red_release_u64(st.bar64, 1ull);
+        unsigned int spins = 0; unsigned long long t0 = 0;
+        while (ld_acquire_u64(st.bar64) < target) {
+            if ((++spins & 1023u) == 0u) {
+                unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t; else if (t - t0 > 8000000000ull) __trap();
+            }
+        }
+        __threadfence();
+    }
+    t5_bar_sync(1, T5_EPI_THREADS);
+}
+
+template <int NC>
+__device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, unsigned int bar0, unsigned int tmem,
+                            unsigned int G, unsigned long long bar_base) {
+    constexpr int KT2 = 16 * NC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp >> 2, rq = warp & 3, row = 32 * rq + lane;
+    const int g0 = t5_g0<NC>(q), ng = t5_ng<NC>(q), col0 = 8 * g0;
+    const unsigned int lane_base = (unsigned int)(32 * rq) << 16;
+    const float2* cK = reinterpret_cast<const float2*>(smem + t5_off_ck(NC));
+    const float2* pS = reinterpret_cast<const float2*>(smem + t5_off_ps(NC));
+    float2* xch = reinterpret_cast<float2*>(smem + t5_off_xch(NC));
+    unsigned int bmask = 0u, rmask = 0u, computed = 0u;
+    double objd = 0.0, obje = 0.0;
+    unsigned int t = 0, nblocks_done = 0;
+    unsigned long long bar_next = bar_base;
+    T5Lev lev; lev.w = make_uint4(0u, 0u, 0u, 0u);
+    T5Run run; run.rs = 0.f; run.upto = -1;
+#pragma unroll
+    for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] = 0.f;
+    unsigned int live = 0u;                       // slots whose running rows are being followed
+    bool had_cells = false;                       // D2y holds sums (tensor memory is not cleared by the allocation)
+    for (;;) {
+        const unsigned int s = t % T5_NZ, d = t & 1u;
+        t5_wait(bar0 + 8u * (T5_B_ZFULL + s), (t / T5_NZ) & 1u);
+        const unsigned char* meta = smem + t5_off_meta(NC) + s * 1024;
+        const int* hdr = reinterpret_cast<const int*>(meta + T5_META_HDR);
+        const unsigned int flags = (unsigned int)hdr[T5_H_FLAGS], tmask = (unsigned int)hdr[T5_H_MASK];
+        const int blk = hdr[T5_H_BLK];
+        const bool empty = (flags & T5_F_EMPTY) != 0u;
+        bool waited_acc = false;
+        if (flags & T5_F_EVICT) {
+            // the slot table starts over with this tile: everything accumulated under the old table leaves now
+            if (t > 0) { t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u); t5_fence_after(); }
+            waited_acc = true;
+            t5_flush_o(st, tmem, lev, bmask, blk);
+            t5_flush_t(st, tmem, lev, rmask);
+            t5_fence_before();
+            bmask = 0u; rmask = 0u; computed = 0u; live = 0u;
+        }
+        lev.w = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr + T5_H_LEV) + 16 * q);
+        if (tmask & ~computed) {
+            t5_penalty_rows<NC>(st, mode, smem, lev, run, tmask & ~computed, live, blk);
+            computed |= tmask; live |= tmask;
+        }
+        const unsigned int slotnb = reinterpret_cast<const unsigned short*>(meta + T5_META_SLOTNB)[row];
+        const bool valid = slotnb != 0xFFFFu;
+        const int slot = valid ? (int)(slotnb >> 8) : 0, nb = (int)(slotnb & 255u);
+        const int cell = reinterpret_cast<const int*>(meta)[row];
+        float E[32];
+        // ---- scores of this thread's clusters (an empty tile still hands the accumulator back)
+        t5_wait(bar0 + 8u * (T5_B_SFULL + d), (t >> 1) & 1u);
+        t5_fence_after();
+        if (!empty) {
+            const unsigned int ta = tmem + lane_base + T5_COL_D1 + 128u * d + (unsigned int)col0;
+            t5_ld16(ta, E);
+            if (ng == 4) t5_ld16(ta + 16u, E + 16);
+            else if (ng == 3) t5_ld8(ta + 16u, E + 16);
+            t5_ld_wait();
+        }
+        t5_fence_before();
+        __syncwarp();
+        if (lane == 0) t5_arrive(bar0 + 8u * (T5_B_SFREE + d));
+        if (!empty) {
+            // ---- S = exp(-dist / sigma) (harmony.py:466-467) times the penalty (harmony.py:500)
+            float ss = 0.f, sp = 0.f, sd = 0.f, se = 0.f, sg = 0.f;
+            const float2* pr = pS + slot * KT2 + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g < ng) {
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2) {
+                        const float4 ck = *reinterpret_cast<const float4*>(cK + col0 + 8 * g + 2 * e2);
+                        const float4 pp = *reinterpret_cast<const float4*>(pr + 8 * g + 2 * e2);
+                        {
+                            const float dist = fmaf(E[8 * g + 2 * e2], -1.9073486328125e-6f, 2.0f);      // 2 (1 - z.y); scores carry 2^20
+                            const float sv = ex2_approx(dist * ck.x);
+                            const float ev = sv * pp.x;
+                            ss += sv; sp += ev;
+                            sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.y, se); sg = fmaf(ev, ck.y, sg);
+                            E[8 * g + 2 * e2] = ev;
+                        }
+                        {
+                            const float dist = fmaf(E[8 * g + 2 * e2 + 1], -1.9073486328125e-6f, 2.0f);
+                            const float sv = ex2_approx(dist * ck.z);
+                            const float ev = sv * pp.z;
+                            ss += sv; sp += ev;
+                            sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.w, se); sg = fmaf(ev, ck.w, sg);
+                            E[8 * g + 2 * e2 + 1] = ev;
+                        }
+                    }
+                }
+            }
+            // ---- the four threads of a cell meet: sums over all clusters
+            float2* xs = xch + (t & 1u) * 512;
+            xs[q * 128 + row] = make_float2(ss, sp);
+            t5_bar_sync(2 + rq, 128);
+            float sst = 0.f, spt = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) { const float2 u = xs[qq * 128 + row]; sst += u.x; spt += u.y; }
+            // R = (S / sum S) pen / max(sum (S / sum S) pen, 1e-8)   (harmony.py:468, :500-503)
+            const float is = 1.f / sst;
+            const float sc = valid ? is / fmaxf(spt * is, 1e-8f) : 0.f;
+            if (valid) {
+                // sum_k r dist and sum_k sigma r ln r with ln r = -dist / sigma + ln pen + ln sc (harmony.py:399-402)
+                objd += (double)(sc * sd);
+                obje += (double)(sc * (se - sd + (lg2_approx(sc) * 0.6931471805599453f) * sg));
+            }
+            // ---- operand tiles of the accumulation: wait until the previous tile's MMAs have read them
+            if (t > 0 && !waited_acc) t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u);
+            const float sc1024 = sc * HMY_OPSCALE;
+            unsigned char* Rh = smem + T5_OFF_RH + (row >> 3) * T5_R_LBO + (row & 7) * 16;
+            float* Rg = st.R + (size_t)cell * st.Kp;
+            const bool wr = st.write_R && valid;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g < ng) {
+                    uint4 hi, lo;
+                    split2(E[8 * g] * sc1024, E[8 * g + 1] * sc1024, hi.x, lo.x);
+                    split2(E[8 * g + 2] * sc1024, E[8 * g + 3] * sc1024, hi.y, lo.y);
+                    split2(E[8 * g + 4] * sc1024, E[8 * g + 5] * sc1024, hi.z, lo.z);
+                    split2(E[8 * g + 6] * sc1024, E[8 * g + 7] * sc1024, hi.w, lo.w);
+                    *reinterpret_cast<uint4*>(Rh + (g0 + g) * T5_R_SBO) = hi;
+                    *reinterpret_cast<uint4*>(Rh + T5_SZ_RPART + (g0 + g) * T5_R_SBO) = lo;
+                    if (wr) {
+                        const int c = col0 + 8 * g;
+                        if (c < st.Kp) *reinterpret_cast<float4*>(Rg + c) = make_float4(E[8 * g] * sc, E[8 * g + 1] * sc, E[8 * g + 2] * sc, E[8 * g + 3] * sc);
+                        if (c + 4 < st.Kp) *reinterpret_cast<float4*>(Rg + c + 4) = make_float4(E[8 * g + 4] * sc, E[8 * g + 5] * sc, E[8 * g + 6] * sc, E[8 * g + 7] * sc);
+                    }
+                }
+            }
+            {
+                // one-hot of the cell's block in the next round: quarter q writes columns [8 q, 8 q + 8)
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                if (valid && (nb >> 3) == q) {
+                    const unsigned int h = (nb & 1) ? 0x3C000000u : 0x3C00u;
+                    const int p = (nb & 7) >> 1;
+                    w.x = p == 0 ? h : 0u; w.y = p == 1 ? h : 0u; w.z = p == 2 ? h : 0u; w.w = p == 3 ? h : 0u;
+                }
+                *reinterpret_cast<uint4*>(smem + T5_OFF_NB + q * T5_R_SBO + (row >> 3) * T5_R_LBO + (row & 7) * 16) = w;
+            }
+            bmask |= tmask; rmask |= tmask; had_cells = true;
+        } else {
+            if (t > 0 && !waited_acc) t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u);
+        }
+        t5_fence_async();
+        __syncwarp();
+        if (lane == 0) t5_arrive(bar0 + 8u * T5_B_RFULL);
+        ++t;
+        if (flags & T5_F_LAST_BLOCK) {
+            // ---- end of the block: its sums join the running O, the next block's removed sums leave it
+            t5_wait(bar0 + 8u * T5_B_ODONE, nblocks_done & 1u);
+            t5_fence_after();
+            ++nblocks_done;
+            t5_flush_o(st, tmem, lev, bmask, blk);
+            bmask = 0u; computed = 0u;
+            const bool last = (flags & T5_F_LAST_ROUND) != 0u;
+            if (!last) {
+                t5_fence_before();
+                t5_grid_barrier(st, bar_next += G);
+            } else {
+                // ---- end of the round: centroid sums, next round's removed sums, objective sums
+                t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u);
+                t5_fence_after();
+                t5_flush_t(st, tmem, lev, rmask);
+                const int dt = (st.d + 15) >> 4;
+                if (q < dt && had_cells) {
+                    float v[16];
+                    t5_ld16(tmem + lane_base + T5_COL_Y + 16u * q, v);
+                    t5_ld_wait();
+                    if (row < st.K) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int jj = 16 * q + j;
+                            if (jj < st.d && v[j] != 0.f) atomicAdd(&st.Yacc[(size_t)row * st.dp + jj], (double)v[j] * (double)HMY_ACCSCALE);
+                        }
+                    }
+                }
+                const double a = warp_sum_d(objd), b = warp_sum_d(obje);
+                if (lane == 0) { atomicAdd(&st.obj[0], a); atomicAdd(&st.obj[1], b); }
+                t5_fence_before();
+                t5_grid_barrier(st, bar_next += G);
+                break;
+            }
+        }
+    }
+    // ---- after the last barrier: every CTA finishes its slice of the small tables
+    {
+        // O of the finished stage = what its blocks put back (harmony.py:506-507 over all blocks; drift-free);
+        // cross-entropy term of the objective (harmony.py:404-411 collapsed to K x B)
+        const int nblocks = (mode == 1) ? 1 : st.nblk;
+        const size_t nBK = (size_t)st.B * st.K;
+        const float* DnewR = st.Dnew + (size_t)st.nblk * nBK;
+        const int n = (int)nBK;
+        const int e0 = (int)((long long)blockIdx.x * n / G), e1 = (int)((long long)(blockIdx.x + 1) * n / G);
+        double part = 0.0;
+        for (int e = e0 + tid; e < e1; e += T5_EPI_THREADS) {
+            const int b = e / st.K, k = e - b * st.K;
+            double o = 0.0, rs = 0.0;
+            for (int i = 0; i < nblocks; ++i) { o += (double)__ldcg(&st.Dnew[(size_t)i * nBK + e]); rs += (double)__ldcg(&DnewR[(size_t)i * st.K + k]); }
+            st.O[e] = o;
+            const float oc = fmaxf((float)o, 1e-8f), ec = fmaxf((float)(rs * (double)st.Pr_b[b]), 1e-8f);
+            part += (double)st.sigma[k] * (double)st.theta[b] * (double)logf((oc + ec) / ec) * o;
+        }
+        part = warp_sum_d(part);
+        if (lane == 0 && part != 0.0) atomicAdd(&st.obj[2], part);
+        // row sums the next round starts from, unit centroids of the next round (harmony.py:443-444)
+        for (int k = blockIdx.x * T5_EPI_WARPS + warp; k < st.K; k += G * T5_EPI_WARPS) {
+            double rs = (lane < nblocks) ? (double)__ldcg(&DnewR[(size_t)lane * st.K + k]) : 0.0;
+            rs = warp_sum_d(rs);
+            if (lane == 0) st.Rsum_next[k] = rs;
+            double y0 = (lane < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + lane]) : 0.0;
+            double y1 = (lane + 32 < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + lane + 32]) : 0.0;
+            const double inv = 1.0 / sqrt(warp_sum_d(y0 * y0 + y1 * y1));
+            if (lane < st.dp) st.Ynext[(size_t)k * st.dp + lane] = (lane < st.d) ? (float)(y0 * inv) : 0.f;
+            if (lane + 32 < st.dp) st.Ynext[(size_t)k * st.dp + lane + 32] = (lane + 32 < st.d) ? (float)(y1 * inv) : 0.f;
+        }
+    }
+}
+
+// ---- kernel -----------------------------------------------------------------------------------------------------------
+// mode 0: one k-means round; mode 1: the assignment of init_cluster (harmony.py:377-392: no penalty, all cells,
+// storage order).  bar_base: value of the grid-barrier counter when the launch starts.
+template <int NC>
+__global__ void __launch_bounds__(T5_THREADS, 1) k_round_tc5(HmyDev st, int mode, unsigned long long bar_base) {
+    extern __shared__ __align__(1024) unsigned char smem_t5[];
+    unsigned char* const smem = smem_t5;
+    constexpr int KT2 = 16 * NC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned int G = gridDim.x;
+    const unsigned int bar0 = smem_u32(smem + t5_off_bar(NC));
+    unsigned int* s_tmem = reinterpret_cast<unsigned int*>(smem + t5_off_bar(NC) + 128);
+    if (warp == T5_WARP_MMA) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "n"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 3; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * (T5_B_ZFULL + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * (T5_B_ACC + i)));
+        }
+        for (int i = 0; i < 2; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * (T5_B_SFULL + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * (T5_B_SFREE + i)), "r"(T5_EPI_WARPS));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8u * T5_B_RFULL), "r"(T5_EPI_WARPS));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8u * T5_B_ODONE));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // ---- round constants: centroids as fp16 hi/lo (K-major core matrices), per-cluster constants, zeroed tiles
+    for (int i = tid; i < KT2 * 32; i += T5_THREADS) {
+        const int k = i >> 5, j = 2 * (i & 31);
         float y0 = 0.f, y1 = 0.f;
         if (k < st.K) {
             if (j < st.dp) y0 = st.Yhat[(size_t)k * st.dp + j] * HMY_OPSCALE;
@@ -196,368 +793,32 @@ __device__ void tc5_load_round_constants(Tc5Ctx<NC>& c, const HmyDev& st, float*
         }
         unsigned int hi, lo;
         split2(y0, y1, hi, lo);
-        const int off = (k >> 3) * TC5_Y_SBO + (j >> 3) * TC5_Y_LBO + (k & 7) * 16 + (j & 7) * 2;
-        *reinterpret_cast<unsigned int*>(c.Yh() + off) = hi;
-        *reinterpret_cast<unsigned int*>(c.Yl() + off) = lo;
+        const int off = (k >> 3) * T5_SBO_K + (j >> 3) * T5_LBO_K + (k & 7) * 16 + (j & 7) * 2;
+        *reinterpret_cast<unsigned int*>(smem + T5_OFF_YH + off) = hi;
+        *reinterpret_cast<unsigned int*>(smem + t5_off_yl(NC) + off) = lo;
     }
-    for (int i = tid; i < st.B * KT2; i += TC5_TILE) { c.Ps()[i] = 0.f; Os[i] = 0.f; }
-    for (int b = tid; b < st.B; b += TC5_TILE) { sPrb[b] = st.Pr_b[b]; sTheta[b] = st.theta[b]; }
-    // t = c2 - acc * c1 is (dist / sigma) * log2(e); c2 = c1 * 2^20; dist = t * c3; sigma ln r = c3 lg2 r
-    for (int k = tid; k < KT2; k += TC5_TILE) {
-        const float sg = (k < st.K) ? st.sigma[k] : 1.f;
-        c.c1()[k] = (k < st.K) ? (2.0f * 1.4426950408889634f / sg) * HMY_ACCSCALE : 0.f;
-        c.c3()[k] = (k < st.K) ? sg * 0.6931471805599453f : 0.f;
+    for (int k = tid; k < KT2; k += T5_THREADS) {
+        // clusters beyond K: exp2(dist * -1e4) = 0 keeps them out of every sum
+        const float sg = (k < st.K) ? st.sigma[k] : 0.f;
+        reinterpret_cast<float2*>(smem + t5_off_ck(NC))[k] = make_float2((k < st.K) ? -1.4426950408889634f / sg : -1.0e4f, sg);
     }
-    // Z tiles: the PCs beyond dp are never written again and must read as zero; R tiles: phase 0 aliases them
-    uint4* z = reinterpret_cast<uint4*>(c.Zh());
-    for (int i = tid; i < 2 * TC5_TILE * TC5_DP * 2 / 16; i += TC5_TILE) z[i] = make_uint4(0u, 0u, 0u, 0u);                 // Zh | Zl
-    uint4* r = reinterpret_cast<uint4*>(c.Rh());
-    for (int i = tid; i < (2 * TC5_KM * TC5_TILE * 2 + TC5_NB * TC5_TILE * 2) / 16; i += TC5_TILE) r[i] = make_uint4(0u, 0u, 0u, 0u);   // Rh | Rl | Ot
-}
-
-// Stage one tile -- ids / levels of its cells (registers: thread = cell), the one-hot level rows, the Z_cos
-// rows as fp16 hi/lo -- and issue its scoring.  Independent of the penalty table, so the first tile of the
-// NEXT block is staged and scored before the grid barrier is waited on.
-// trb: first of 5 timeline slots of this tile (>= HMY_TRACE_SLOTS: none): stage begin, operands published,
-// scores ready, epilogue done, R tile published.
-template <int NC>
-__device__ void tc5_stage_tile(Tc5Ctx<NC>& c, const HmyDev& st, const int* list, long long tb, int nt, int trb) {
-    const int tid = threadIdx.x;
-    hmy_trace(st, trb);
-    tc5_wait_acc(c);
-    c.valid = tid < nt;
-    int cell = 0, combo = 0;
-    if (c.valid) { cell = list ? list[tb + tid] : (int)(tb + tid); combo = st.combo[cell]; }
-    c.cell = cell;
-    c.sCell[tid] = cell;
-    unsigned int mask = 0u;
-#pragma unroll
-    for (int v = 0; v < HMY_MAX_V; ++v) {
-        c.lev[v] = (v < st.V) ? st.combo_lev[combo * st.V + v] : 0;
-        if (v < st.V && c.valid) mask |= 1u << c.lev[v];
-    }
-    // level rows of this cell: element (level, cell) of the MN-major one-hot tile, 8 levels = one 16-byte core row
-#pragma unroll
-    for (int j = 0; j < TC5_NB / 8; ++j) {
-        const unsigned int m8 = (mask >> (8 * j)) & 0xFFu;
-        uint4 w;
-        w.x = ((m8 & 1u) ? 0x3C00u : 0u) | ((m8 & 2u) ? 0x3C000000u : 0u);
-        w.y = ((m8 & 4u) ? 0x3C00u : 0u) | ((m8 & 8u) ? 0x3C000000u : 0u);
-        w.z = ((m8 & 16u) ? 0x3C00u : 0u) | ((m8 & 32u) ? 0x3C000000u : 0u);
-        w.w = ((m8 & 64u) ? 0x3C00u : 0u) | ((m8 & 128u) ? 0x3C000000u : 0u);
-        *reinterpret_cast<uint4*>(c.Ot() + j * TC5_O_SBO + (tid >> 3) * TC5_O_LBO + (tid & 7) * 16) = w;
-    }
-    __syncthreads();
     {
-        // gather: a batch of loads per thread is issued before its first conversion / store
-        constexpr int ZU = 8;
-        const int dp = st.dp, dp4 = dp >> 2, total = nt * dp4;
-        for (int base = 0; base < total; base += ZU * TC5_TILE) {
-            float4 zr[ZU];
-#pragma unroll
-            for (int u = 0; u < ZU; ++u) {
-                const int i = base + tid + u * TC5_TILE;
-                if (i < total) {
-                    const int row = hmy_div(i, c.mg_dp4), c4 = i - row * dp4;
-                    zr[u] = __ldg(reinterpret_cast<const float4*>(st.Zcos + (size_t)c.sCell[row] * dp) + c4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < ZU; ++u) {
-                const int i = base + tid + u * TC5_TILE;
-                if (i < total) {
-                    const int row = hmy_div(i, c.mg_dp4), c4 = i - row * dp4;
-                    uint2 hi, lo;
-                    split2(zr[u].x * HMY_OPSCALE, zr[u].y * HMY_OPSCALE, hi.x, lo.x);
-                    split2(zr[u].z * HMY_OPSCALE, zr[u].w * HMY_OPSCALE, hi.y, lo.y);
-                    const int off = (row >> 3) * TC5_Z_SBO_K + (c4 >> 1) * TC5_Z_LBO_K + (row & 7) * 16 + (c4 & 1) * 8;
-                    *reinterpret_cast<uint2*>(c.Zh() + off) = hi;
-                    *reinterpret_cast<uint2*>(c.Zl() + off) = lo;
-                }
-            }
-        }
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        for (int i = tid; i < T5_OFF_ONES / 16; i += T5_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);        // Z stages | R tiles | one-hot tile
+        unsigned int* ones = reinterpret_cast<unsigned int*>(smem + T5_OFF_ONES);
+        for (int i = tid; i < 128; i += T5_THREADS) ones[i] = 0x3C003C00u;
+        float2* ps = reinterpret_cast<float2*>(smem + t5_off_ps(NC));
+        for (int i = tid; i < T5_SLOTS * KT2; i += T5_THREADS) ps[i] = make_float2(0.f, 0.f);
     }
-    tc5_publish();
-    hmy_trace(st, trb + 1);
-    if (tid == 0) {
-        const unsigned int sb = smem_u32(c.base), id_score = tc5_idesc(TC5_TILE, 16 * NC, 0, 0);
-        const unsigned long long dZh = tc5_desc(sb + TC5_OFF_ZH, TC5_Z_LBO_K, TC5_Z_SBO_K), dZl = tc5_desc(sb + TC5_OFF_ZL, TC5_Z_LBO_K, TC5_Z_SBO_K);
-        const unsigned long long dYh = tc5_desc(sb + TC5_OFF_YH, TC5_Y_LBO, TC5_Y_SBO), dYl = tc5_desc(sb + tc5_off_yl(NC), TC5_Y_LBO, TC5_Y_SBO);
-        for (int ks = 0; ks < c.dt; ++ks) {
-            const unsigned long long o = (unsigned long long)((ks * 2 * TC5_Z_LBO_K) >> 4);     // two 8-wide PC chunks per K = 16
-            tc5_mma(c.tmem, dZl + o, dYh + o, id_score, ks > 0 ? 1u : 0u);
-            tc5_mma(c.tmem, dZh + o, dYl + o, id_score, 1u);
-            tc5_mma(c.tmem, dZh + o, dYh + o, id_score, 1u);
-        }
-        tc5_commit(&c.bar[0]);
-    }
-}
-
-// Epilogue of the staged tile (thread = cell) and its contribution to the sums.
-template <int NC>
-__device__ void tc5_finish_tile(Tc5Ctx<NC>& c, const HmyDev& st, bool init, int nt, int trb) {
-    constexpr int KT2 = 16 * NC;
-    const int tid = threadIdx.x, K = st.K, Kp = st.Kp, V = st.V;
-    tc5_wait(&c.bar[0], c.ph_score & 1u);
-    c.ph_score++;
-    hmy_trace(st, trb + 2);
-    float E[KT2];
-    float ss = 0.f, sp = 0.f, sd = 0.f;
-    // ---- S = exp(-dist/sigma) (harmony.py:466-467), times the penalty (harmony.py:500)
-#pragma unroll
-    for (int ch = 0; ch < NC; ++ch) {
-        float a[16];
-        tc5_ld16(c.tmem + c.lane_base + (unsigned int)(16 * ch), a);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int col = 16 * ch + 4 * q;
-            const float4 k1 = *reinterpret_cast<const float4*>(c.c1() + col);
-            const float4 k3 = *reinterpret_cast<const float4*>(c.c3() + col);
-            float4 pen = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (!init) {
-                pen = *reinterpret_cast<const float4*>(c.Ps() + c.lev[0] * KT2 + col);
-#pragma unroll
-                for (int v = 1; v < HMY_MAX_V; ++v)            // more covariates: the factors add (harmony.py:500)
-                    if (v < V) {
-                        const float4 u = *reinterpret_cast<const float4*>(c.Ps() + c.lev[v] * KT2 + col);
-                        pen.x += u.x; pen.y += u.y; pen.z += u.z; pen.w += u.w;
-                    }
-            }
-            const float k1v[4] = {k1.x, k1.y, k1.z, k1.w}, k3v[4] = {k3.x, k3.y, k3.z, k3.w}, pv[4] = {pen.x, pen.y, pen.z, pen.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                // t = (dist / sigma) log2 e >= 0; columns beyond K give s = 0
-                const float t = fmaf(-a[4 * q + e], k1v[e], k1v[e] * 1048576.0f);
-                const float s = (col + e < K) ? ex2_approx(-t) : 0.f;
-                ss += s;
-                const float ev = s * pv[e];
-                sp += ev;
-                sd = fmaf(k3v[e], ev * t, sd);                  // dist = t * c3: sum S*pen*dist for the objective (harmony.py:399)
-                E[col + e] = ev;
-            }
-        }
-    }
-    // R = (S/sumS) pen / max(sum (S/sumS) pen, 1e-8)   (harmony.py:468, :500-503)
-    const float is = 1.f / ss;
-    const float sc = c.valid ? is / fmaxf(sp * is, 1e-8f) : 0.f;
-    float* Rg = st.R + (size_t)c.cell * Kp;
-    float oe = 0.f;
-#pragma unroll
-    for (int c0 = 0; c0 < KT2; c0 += 8) {
-        const float4 k3a = *reinterpret_cast<const float4*>(c.c3() + c0), k3b = *reinterpret_cast<const float4*>(c.c3() + c0 + 4);
-        const float k3v[8] = {k3a.x, k3a.y, k3a.z, k3a.w, k3b.x, k3b.y, k3b.z, k3b.w};
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            r[j] = E[c0 + j] * sc;
-            oe = fmaf(k3v[j], (r[j] > 0.f ? r[j] * lg2_approx(r[j]) : 0.f), oe);   // sigma r ln r (harmony.py:402)
-        }
-        if (c.valid) {
-            if (c0 < Kp) *reinterpret_cast<float4*>(Rg + c0) = make_float4(r[0], r[1], r[2], r[3]);
-            if (c0 + 4 < Kp) *reinterpret_cast<float4*>(Rg + c0 + 4) = make_float4(r[4], r[5], r[6], r[7]);
-        }
-        uint4 hi, lo;
-        split2(r[0] * HMY_OPSCALE, r[1] * HMY_OPSCALE, hi.x, lo.x);
-        split2(r[2] * HMY_OPSCALE, r[3] * HMY_OPSCALE, hi.y, lo.y);
-        split2(r[4] * HMY_OPSCALE, r[5] * HMY_OPSCALE, hi.z, lo.z);
-        split2(r[6] * HMY_OPSCALE, r[7] * HMY_OPSCALE, hi.w, lo.w);
-        const int off = (c0 >> 3) * TC5_R_SBO + (tid >> 3) * TC5_R_LBO + (tid & 7) * 16;      // element (cluster c0.., cell tid)
-        *reinterpret_cast<uint4*>(c.Rh() + off) = hi;
-        *reinterpret_cast<uint4*>(c.Rl() + off) = lo;
-    }
-    if (c.valid) { c.objd += (double)(sc * sd); c.obje += (double)oe; }
-    hmy_trace(st, trb + 3);
-    tc5_publish();
-    hmy_trace(st, trb + 4);
-    // ---- sums over the cells of the tile (K-dim = cells, 16 per step)
-    if (tid == 0) {
-        const unsigned int sb = smem_u32(c.base), id_y = tc5_idesc(TC5_KM, TC5_DP, 1, 1), id_o = tc5_idesc(TC5_KM, TC5_NB, 1, 1);
-        const unsigned long long dRh = tc5_desc(sb + TC5_OFF_RH, TC5_R_LBO, TC5_R_SBO), dRl = tc5_desc(sb + TC5_OFF_RL, TC5_R_LBO, TC5_R_SBO);
-        const unsigned long long dZh = tc5_desc(sb + TC5_OFF_ZH, TC5_Z_LBO_MN, TC5_Z_SBO_MN), dZl = tc5_desc(sb + TC5_OFF_ZL, TC5_Z_LBO_MN, TC5_Z_SBO_MN);
-        const unsigned long long dOt = tc5_desc(sb + TC5_OFF_OT, TC5_O_LBO, TC5_O_SBO);
-        const int ksteps = (nt + 15) >> 4;
-        for (int ks = 0; ks < ksteps; ++ks) {
-            const unsigned long long ro = (unsigned long long)((ks * 2 * TC5_R_LBO) >> 4);
-            const unsigned long long zo = (unsigned long long)((ks * 2 * TC5_Z_LBO_MN) >> 4);
-            const unsigned long long oo = (unsigned long long)((ks * 2 * TC5_O_LBO) >> 4);
-            tc5_mma(c.tmem + TC5_COL_Y, dRl + ro, dZh + zo, id_y, (c.y_started || ks > 0) ? 1u : 0u);
-            tc5_mma(c.tmem + TC5_COL_Y, dRh + ro, dZl + zo, id_y, 1u);
-            tc5_mma(c.tmem + TC5_COL_Y, dRh + ro, dZh + zo, id_y, 1u);
-            tc5_mma(c.tmem + TC5_COL_O, dRl + ro, dOt + oo, id_o, (c.o_started || ks > 0) ? 1u : 0u);
-            tc5_mma(c.tmem + TC5_COL_O, dRh + ro, dOt + oo, id_o, 1u);
-        }
-        tc5_commit(&c.bar[1]);
-    }
-    c.acc_pending = true; c.y_started = true; c.o_started = true;
-}
-
-// End of a block: thread = cluster adds its row of the level sums to Dnew[blk] / Ofresh (harmony.py:506-507)
-template <int NC>
-__device__ void tc5_flush_block(Tc5Ctx<NC>& c, const HmyDev& st, int blk) {
-    if (!c.o_started) return;
-    tc5_wait_acc(c);
-    const int tid = threadIdx.x;
-    float v0[16], v1[16];
-    tc5_ld16(c.tmem + c.lane_base + (unsigned int)TC5_COL_O, v0);
-    tc5_ld16(c.tmem + c.lane_base + (unsigned int)(TC5_COL_O + 16), v1);
-    if (tid < st.K) {
-        float* dn = st.Dnew + (size_t)blk * st.B * st.K + tid;
-        double* of = st.Ofresh + tid;
-#pragma unroll
-        for (int b = 0; b < TC5_NB; ++b) {
-            const float x = (b < 16 ? v0[b & 15] : v1[b & 15]) * (1.0f / HMY_OPSCALE);
-            if (b < st.B && x != 0.f) {
-                atomicAdd(dn + (size_t)b * st.K, x);
-                atomicAdd(of + (size_t)b * st.K, (double)x);
-            }
-        }
-    }
-    c.o_started = false;
-}
-
-// One block of update_R (harmony.py:495-509) for this CTA's cells, or the init assignment
-// (harmony.py:380-389) when init = true.  staged_tb: first list index of the tile tc5_stage_tile already
-// prepared and scored (-1: none).
-template <int NC>
-__device__ void tc5_process_block(Tc5Ctx<NC>& c, const HmyDev& st, int blk, const int* list,
-                                  long long lbeg, long long lend, bool init, long long staged_tb) {
-    int trb = (blk == 5 && !init) ? 64 : HMY_TRACE_SLOTS;          // per-tile timeline of block 5 (option "trace")
-    for (long long tb = lbeg; tb < lend; tb += TC5_TILE) {
-        const int nt = (int)min((long long)TC5_TILE, lend - tb);
-        if (tb != staged_tb) tc5_stage_tile(c, st, list, tb, nt, trb);
-        tc5_finish_tile(c, st, init, nt, trb);
-        if (trb < HMY_TRACE_SLOTS - 10) trb += 5; else trb = HMY_TRACE_SLOTS;
-    }
-    tc5_flush_block(c, st, blk);
-}
-
-// End of a round: centroid sums (thread = cluster) and objective sums
-template <int NC>
-__device__ void tc5_flush_round(Tc5Ctx<NC>& c, const HmyDev& st) {
-    const int tid = threadIdx.x;
-    if (c.y_started) {
-        tc5_wait_acc(c);
-#pragma unroll
-        for (int ch = 0; ch < TC5_DP / 16; ++ch) {
-            float v[16];
-            tc5_ld16(c.tmem + c.lane_base + (unsigned int)(TC5_COL_Y + 16 * ch), v);
-            if (tid < st.K) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int jj = 16 * ch + j;
-                    if (jj < st.d && v[j] != 0.f) atomicAdd(&st.Yacc[(size_t)tid * st.dp + jj], (double)v[j] * (double)HMY_ACCSCALE);
-                }
-            }
-        }
-        c.y_started = false;
-    }
-    const double a = warp_sum_d(c.objd), b = warp_sum_d(c.obje);
-    if ((tid & 31) == 0) { atomicAdd(&st.obj[0], a); atomicAdd(&st.obj[1], b); }
-    c.objd = 0.0; c.obje = 0.0;
-}
-
-// ---- kernel -----------------------------------------------------------------------------------------
-template <int NC, bool FUSED>
-__global__ void __launch_bounds__(TC5_TILE, 1) k_round_tc5(HmyDev st, int mode, unsigned int gen_base) {
-    extern __shared__ __align__(1024) unsigned char smem_tc5[];
-    unsigned char* const smem = smem_tc5;
-    __shared__ __align__(8) unsigned long long s_bar[2];
-    __shared__ unsigned int s_tmem;
-    const Tc5Smem p = tc5_smem_plan(st.B, NC);
-    const bool multi_any = FUSED && st.xworld > 1;
-    const unsigned int G = multi_any ? gridDim.x - 1u : gridDim.x;          // worker CTAs
-    double* sRow = (double*)(smem + p.off_misc);
-    double* sRed = sRow + 256;
-    int* sFlag = (int*)(sRed + 8);
-    if (multi_any && blockIdx.x == G) {
-        comm_cta_main(st, mode, gen_base, G, sRow, sRed);
-        return;
-    }
-    const int tid = threadIdx.x, warp = tid >> 5;
-
-    // the parts of the mma.sync kernel that are reused unchanged (phase 0, per-CTA tables) see this context
-    MmaCtx<2 * NC, 1> m;
-    m.Rh = (__half*)(smem + p.off_Rh); m.Rl = (__half*)(smem + p.off_Rl);
-    m.sCell = (int*)(smem + p.off_cell);
-    m.Ps = (float*)(smem + p.off_Ps); m.Os = (float*)(smem + p.off_Os);
-    m.sPrb = (float*)(smem + p.off_prb); m.sTheta = m.sPrb + st.B;
-    m.RSH = p.RSH; m.KT2 = p.KT2;
-    m.mg_kp4 = hmy_magic(st.Kp >> 2); m.mg_K = hmy_magic(st.K);
-
-    Tc5Ctx<NC> c;
-    c.base = smem;
-    c.sCell = m.sCell;
-    c.bar = s_bar;
-    c.ph_score = 0u; c.ph_acc = 0u; c.acc_pending = false; c.y_started = false; c.o_started = false;
-    c.dt = (st.d + 15) >> 4;
-    c.mg_dp4 = hmy_magic(st.dp >> 2);
-    c.cell = 0; c.valid = false;
-#pragma unroll
-    for (int v = 0; v < HMY_MAX_V; ++v) c.lev[v] = 0;
-    c.objd = 0.0; c.obje = 0.0;
-
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "n"(TC5_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[0])));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar[1])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G;
-    hmy_trace(st, 0);
-    tc5_load_round_constants(c, st, m.Os, m.sPrb, m.sTheta);
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    t5_fence_async();
+    t5_fence_before();
     __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    c.tmem = s_tmem;
-    c.lane_base = (unsigned int)(32 * warp) << 16;
-
-    if (mode == 1) {
-        tc5_process_block(c, st, 0, nullptr, c0, c1, true, -1);
-        tc5_flush_round(c, st);
-        if (multi_any) worker_barrier(st, gen_base + 1u);
-        else grid_barrier_serial(st, G, gen_base + 1u, sFlag, [&]() { serial_finalize(st, 1, sRow, sRed); });
-    } else {
-        if (st.nblk <= 32) mma_phase0(m, st, c0, c1);
-        hmy_trace(st, 1);
-        unsigned int gen = gen_base + 1u;
-        mma_load_O(m, st);                       // O is only written by the finalize of the previous launch
-        long long staged = -1;
-        {
-            long long nb, ne;
-            block_share(st, 0, blockIdx.x, G, nb, ne);
-            if (nb < ne) { tc5_stage_tile(c, st, st.list, nb, (int)min((long long)TC5_TILE, ne - nb), HMY_TRACE_SLOTS); staged = nb; }
-        }
-        const bool multi = multi_any && !st.xrelaxed;      // exact mode: one table exchange per block
-        if (multi_any) worker_barrier(st, gen++);          // comm CTA: all Told sums are in (+ exchange)
-        else grid_barrier(st, G, gen++);
-        hmy_trace(st, 2);
-        for (int blk = 0; blk < st.nblk; ++blk) {
-            mma_update_tables(m, st, blk, multi);
-            hmy_trace(st, 3 + 3 * blk);
-            long long lb, le;
-            block_share(st, blk, blockIdx.x, G, lb, le);
-            tc5_process_block(c, st, blk, st.list, lb, le, false, staged);
-            hmy_trace(st, 4 + 3 * blk);
-            staged = -1;
-            if (blk + 1 < st.nblk) {        // next block's first tile: stage and score before waiting at the barrier
-                long long nb, ne;
-                block_share(st, blk + 1, blockIdx.x, G, nb, ne);
-                if (nb < ne) { tc5_stage_tile(c, st, st.list, nb, (int)min((long long)TC5_TILE, ne - nb), blk + 1 == 5 ? 64 : HMY_TRACE_SLOTS); staged = nb; }
-                if (multi_any) worker_barrier(st, gen++);
-                else grid_barrier(st, G, gen++);
-            } else {
-                tc5_flush_round(c, st);
-                if (multi_any) worker_barrier(st, gen++);
-                else grid_barrier_serial(st, G, gen++, sFlag, [&]() { serial_finalize(st, 0, sRow, sRed); });
-            }
-            hmy_trace(st, 5 + 3 * blk);
-        }
-    }
-    // every MMA has been waited for (flush_block / flush_round); give the tensor memory back
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    t5_fence_after();
+    const unsigned int tmem = *s_tmem;
+    if (warp == T5_WARP_PROD) t5_producer<NC>(st, mode, smem, bar0, G);
+    else if (warp == T5_WARP_MMA) { if (lane == 0) t5_mma_thread<NC>(st, smem, bar0, tmem); __syncwarp(); }
+    else t5_epilogue<NC>(st, mode, smem, bar0, tmem, G, bar_base);
+    t5_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(c.tmem), "n"(TC5_TMEM_COLS));
+    if (warp == T5_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));
 }

@@ -347,8 +347,17 @@ class Harmony:
                 self._engine.comm_attach(comm.rank, comm.world, handles)
             comm.dist.barrier(group=comm.group)
         self.allocate_buffers()
+        # Engines that run one round ahead keep R in tensor memory / registers and store it to HBM only when asked:
+        # inside cluster() that is after the rounds the loop can stop at (harmony.py:455-458); stages called one by
+        # one (init_cluster, kmeans_round, update_R) always store it.
+        self._lazy_R = bool(getattr(self._engine, "lookahead", False))
         if run:
+            rounds_follow = self.max_iter_harmony > 0 and self.max_iter_kmeans > 0
+            if self._lazy_R and rounds_follow:
+                self._engine.set_option("write_r", 0)          # nothing reads R between init and the first round
             self.init_cluster(random_state, init_centroids)
+            if self._lazy_R:
+                self._engine.set_option("write_r", 1)
             self.harmonize(self.max_iter_harmony, self.verbose)
 
     # ------------------------------------------------------------------ gathered reads
@@ -492,6 +501,10 @@ class Harmony:
         if Y0.shape == (self.d, self.K) and self.d != self.K:
             Y0 = Y0.T
         assert Y0.shape == (self.K, self.d), "init_centroids must be K x d"
+        if getattr(self._engine, "lookahead", False) and self.perm_mode == "reference":
+            # the init assignment already groups its sums by the FIRST round's blocks: hand over that permutation
+            # (first draw of the stream, harmony.py:471); every round call then carries the next round's
+            self._engine.queue_perm(self._next_perm())
         self._record_objective(self._engine.init_from_centroids(Y0))
         self.objective_harmony.append(self.objective_kmeans[-1])  # harmony.py:392
 
@@ -518,11 +531,16 @@ class Harmony:
     def cluster(self):
         """harmony.py:437-462."""
         rounds = 0
+        lazy = getattr(self, "_lazy_R", False)
         for i in range(self.max_iter_kmeans):
+            if lazy:      # R must be in HBM after every round the loop can end with
+                self._engine.set_option("write_r", int(i > self.window_size or i == self.max_iter_kmeans - 1))
             self.kmeans_round()
             rounds = i + 1
             if i > self.window_size and self.check_convergence(0):    # :455-458
                 break
+        if lazy:
+            self._engine.set_option("write_r", 1)
         self.kmeans_rounds.append(rounds)                              # :461
         self.objective_harmony.append(self.objective_kmeans[-1])       # :462
 

@@ -91,6 +91,17 @@ int hmy_kmeans_init(hmy_ctx* ctx, uint64_t seed, int max_iter, double tol, float
  * device-side pseudo-random permutation from (seed, round counter). */
 int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double obj[3]);
 
+/* Contexts whose counter "lookahead" is 1 (single-GPU persistent runs on the tensor-memory round kernel) run the
+ * block permutations ONE ROUND AHEAD: a round already accumulates, per block of the NEXT round, the sums that round
+ * will remove from O (harmony.py:491-492), so it must know the next round's blocks.  Call order there:
+ *     hmy_queue_perm(perm of round 0)            (omit with device-side permutations)
+ *     hmy_init_from_centroids(...)
+ *     hmy_kmeans_round(perm of round 1, ...)     runs round 0
+ *     hmy_kmeans_round(perm of round 2, ...)     runs round 1 ...
+ * i.e. the same stream of torch.randperm draws as harmony.py:471, each handed over one call earlier.  With
+ * "lookahead" 0 hmy_kmeans_round takes the permutation of the round it runs and hmy_queue_perm fails. */
+int hmy_queue_perm(hmy_ctx* ctx, const int64_t* perm_host);
+
 /* moe_correct_ridge (harmony.py:535-569): per-cluster ridge regression, Z_corr, Z_cos. */
 int hmy_ridge_correct(hmy_ctx* ctx);
 
@@ -105,9 +116,11 @@ int hmy_synchronize(hmy_ctx* ctx);
  *   "mma"        0/1   tensor-core round kernels (default, d <= 64) vs fp32 SIMT; before hmy_set_params
  *   "ridge_mma"  0/1   tensor-core ridge passes (default, d <= 63) vs fp32 SIMT; before hmy_set_params
  *   "mma_wn"     0/2   force two warps along the cluster axis (A/B runs); before hmy_set_params
- *   "tc5"        0/1   tcgen05 / tensor-memory round kernel for the persistent mode (K <= 128, d <= 64,
- *                      B <= 32, <= 32 blocks; other shapes FAIL); default 0 until validated on hardware;
- *                      before hmy_set_params
+ *   "tc5"        -1/0/1 tcgen05 / tensor-memory round kernel (hmy_round_tc5.cuh; K <= 128, d <= 64, <= 32 blocks,
+ *                      single-GPU persistent mode): -1 = where it applies (default), 0 = never, 1 = required
+ *                      (other shapes FAIL); before hmy_set_params
+ *   "write_r"    0/1   lookahead contexts only: the next stages store R to HBM (default 1).  With 0 the rounds skip
+ *                      the 4K bytes per cell; hmy_ridge_correct and hmy_get(HMY_R) fail until a stage ran with 1
  *   "relaxed"    0/1   fused multi-GPU mode: exchange the K x B table once per round instead of once
  *                      per block (NOT exact; default 0)
  *   "timing"     0/1   CUDA-event timers around the stages (default 1)
@@ -117,7 +130,7 @@ int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value);
 
 /* Counters: "launches" (kernels launched by this library since creation), "rounds",
  * "ridge_passes", "grid", "nblk", "ncombo", "mma", "ridge_mma", "fused", "round_threads",
- * "smem_round", "tc5".  Timers (CUDA events on the context stream, milliseconds, cumulative):
+ * "smem_round", "tc5", "lookahead", "r_valid".  Timers (CUDA events on the context stream, milliseconds, cumulative):
  * "ms_round", "ms_ridge", "ms_init".  Unknown names return -1. */
 int64_t hmy_counter(const hmy_ctx* ctx, const char* name);
 double hmy_timer_ms(hmy_ctx* ctx, const char* name);

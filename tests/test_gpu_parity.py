@@ -115,9 +115,9 @@ def test_tc5_round_matches_mma_round_and_golden(name):
     """K = 40 / two covariates (NC = 4) and K = 100 / one covariate (NC = 7), ragged last tiles, 20 blocks."""
     inp, gold = load_case(name)
     a, _ = _engine_run(inp, options={"tc5": 1}, record=False)
-    b, _ = _engine_run(inp, record=False)
+    b, _ = _engine_run(inp, options={"tc5": 0}, record=False)
     assert a._engine.counter("tc5") == 1 and b._engine.counter("tc5") == 0
-    assert a._engine.counter("round_threads") == 128
+    assert a._engine.counter("round_threads") == 576 and a._engine.counter("lookahead") == 1
     assert list(a.kmeans_rounds) == list(gold["kmeans_rounds"])
     print(f"\n[tc5 {name}] vs mma kernel: Z {rel_max(a.Z_corr, b.Z_corr):.3e} R {rel_max(a.R, b.R):.3e}; "
           f"vs ref fp32: {rel_max(a.Z_corr[gold['final_cells']], gold['Zcorr_final']):.3e}")
