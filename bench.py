@@ -30,6 +30,12 @@ import sys
 import threading
 import time
 
+# The CPU arm runs BLAS / OpenMP code on hosts with > 100 cores: OpenBLAS aborts ("NUM_THREADS exceeded", rc 139 in
+# round 1) when asked for more threads than it was built for, so the pools are capped BEFORE numpy / torch load.
+CPU_THREADS = max(1, min(os.cpu_count() or 1, 32))
+for _v in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+    os.environ.setdefault(_v, str(CPU_THREADS))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -172,62 +178,120 @@ def _oracle_run(w, Y0, n_sample):
     return n_sample / dt, dt, dict(rounds=list(map(int, orc.kmeans_rounds)))
 
 
-_BEST_THREADS = {}
+def load_reference():
+    """The UNMODIFIED reference package staged under baseline/_ref (baseline/stage_reference.py), or None."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_dir, "harmonypy", "harmony.py")):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "baseline"))
+            import stage_reference
+            stage_reference.stage(verbose=False)
+        except Exception:
+            pass
+    if not os.path.exists(os.path.join(ref_dir, "harmonypy", "harmony.py")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    import harmonypy.harmony as rh
+    return rh
 
 
-def cpu_oracle_rate(w, Y0, n_sample):
-    """Oracle port of the reference's CPU algorithm on the first n_sample cells of the workload:
-    init assignment + harmonize to convergence.  The BLAS thread count is tuned first on a small
-    sample (more threads are not faster for these K x n x B shapes; the reference's torch path
-    behaves the same), then the timed sample runs with the best one.
-    Returns (cells/s, seconds, info incl. the thread count used)."""
+def reference_run(rh, w, Y0, n_sample, threads):
+    """One run of the reference's own run_harmony(device='cpu') on the first n_sample cells of the workload.
+    Its sklearn k-means++ call (harmony.py:369-373) is answered with the SAME centroids our arm starts from
+    (the module's KMeans name is pointed at a stub; no reference source is touched), so both arms time the same
+    work: init assignment + harmonize() to the reference's own convergence rule.
+    Returns (seconds of init_cluster + harmonize, seconds of the whole run_harmony call, kmeans_rounds)."""
+    import pandas as pd
+    import torch
+    from harmonypy_b200.synthetic import make_synthetic_arrays
+    torch.set_num_threads(threads)
+    Z, codes = make_synthetic_arrays(max(n_sample, 1), w["d"], w["levels"], seed=SEED, lo=0, hi=n_sample)
+    meta = pd.DataFrame({f"var{v}": [f"v{v}_{c:04d}" for c in codes[v]] for v in range(len(w["levels"]))})
+
+    class GivenCentroids:                      # stands in for sklearn.cluster.KMeans inside the reference module
+        def __init__(self, **kw):
+            pass
+
+        def fit(self, X):
+            self.cluster_centers_ = np.asarray(Y0, dtype=np.float64)
+            return self
+
+    spans = {}
+    orig_init, orig_harm, orig_km = rh.Harmony.init_cluster, rh.Harmony.harmonize, rh.KMeans
+
+    def timed(name, fn):
+        def wrap(self, *a, **k):
+            t = time.perf_counter()
+            r = fn(self, *a, **k)
+            spans[name] = spans.get(name, 0.0) + time.perf_counter() - t
+            return r
+        return wrap
+    rh.KMeans = GivenCentroids
+    rh.Harmony.init_cluster = timed("init", orig_init)
+    rh.Harmony.harmonize = timed("harmonize", orig_harm)
+    try:
+        t0 = time.perf_counter()
+        ho = rh.run_harmony(Z, meta, list(meta.columns), nclust=w["K"], max_iter_harmony=10, max_iter_kmeans=20,
+                            verbose=False, random_state=SEED, device="cpu")
+        _ = ho.Z_corr
+        total = time.perf_counter() - t0
+    finally:
+        rh.KMeans, rh.Harmony.init_cluster, rh.Harmony.harmonize = orig_km, orig_init, orig_harm
+    return spans["init"] + spans["harmonize"], total, list(map(int, ho.kmeans_rounds))
+
+
+def cpu_arm(w, Y0, n_sample):
+    """The CPU arm: the staged reference when present (kind "reference"), else the NumPy port (kind "port").
+    Returns dict(loop_seconds, total_seconds, rounds, kind, cores, sample)."""
+    rh = load_reference()
+    if rh is not None:
+        loop, total, rounds = reference_run(rh, w, Y0, n_sample, CPU_THREADS)
+        return dict(loop_seconds=loop, total_seconds=total, rounds=rounds, kind="reference", cores=CPU_THREADS,
+                    sample=f"unmodified harmonypy.run_harmony(device='cpu', torch fp32, {CPU_THREADS} threads) from baseline/_ref on "
+                           f"the first {n_sample} cells of the workload, same initial centroids as the GPU arm "
+                           f"(its sklearn call is answered with them), init assignment + harmonize to convergence, rounds {rounds}")
     from threadpoolctl import threadpool_limits
-    ncpu = os.cpu_count() or 1
-    key = (w["K"], w["d"], tuple(w["levels"]))
-    if key not in _BEST_THREADS:
-        best, best_rate = ncpu, -1.0
-        for t in sorted({1, 8, 32, ncpu}):
-            if t > ncpu:
-                continue
-            with threadpool_limits(limits=t):
-                rate, _, _ = _oracle_run(w, Y0, min(n_sample, 10_000))
-            if rate > best_rate:
-                best, best_rate = t, rate
-        _BEST_THREADS[key] = best
-    t = _BEST_THREADS[key]
-    with threadpool_limits(limits=t):
+    with threadpool_limits(limits=min(CPU_THREADS, 8)):
         rate, dt, info = _oracle_run(w, Y0, n_sample)
-    info["threads"] = t
-    return rate, dt, info
+    return dict(loop_seconds=dt, total_seconds=dt, rounds=info["rounds"], kind="port", cores=min(CPU_THREADS, 8),
+                sample=f"oracle/harmony_oracle.py (NumPy fp32 port; baseline/_ref is absent) on the first {n_sample} cells, "
+                       f"init assignment + harmonize to convergence, rounds {info['rounds']}")
+
+
+def workload_config(w, world, N_total, mode=None, rounds=None, iters=None):
+    """The `config` object of the JSON line -- identical for both arms of one (workload, n_gpus)."""
+    return {"workload": w["name"], "cells_total": N_total, "cells_per_gpu": w["per_gpu"], "d": w["d"],
+            "levels": w["levels"], "K": w["K"], "parallelism": f"cells sharded over {world} GPU(s)",
+            "perm_mode": "device", "l2": "inputs larger than L2 (R 400 MB + Z 600 MB per GPU), no flush",
+            "init": f"sklearn k-means++ on a {min(N_total, INIT_SUBSAMPLE)}-cell subsample, untimed"}
 
 
 def run_reference(args, w):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is
-    Python and cannot travel to this box) on a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation on this box's host cores, on a bounded sample of the
+    workload (rank 0 only; the other ranks exit without work)."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return
     n_sample = args.cpu_sample
-    Y0 = init_centroids(w, n_sample)
-    times = []
+    N_total = w["per_gpu"] * world
+    Y0 = init_centroids(w, N_total)
+    loops, totals = [], []
     for i in range(args.warmup + args.steps):
-        rate, dt, info = cpu_oracle_rate(w, Y0, n_sample)
+        r = cpu_arm(w, Y0, n_sample)
         if i >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
+            loops.append(r["loop_seconds"]); totals.append(r["total_seconds"])
+    ms = 1e3 * float(np.mean(loops))
     val = n_sample / (ms / 1e3)
-    cores = info.get("threads", os.cpu_count())
     out = {
         "impl": "reference", "metric": "cells/sec to convergence (full Harmony loop)", "value": val,
         "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["name"], "sample": f"first {n_sample} cells of the workload", "K": w["K"], "d": w["d"],
-                   "levels": w["levels"], "rounds": info["rounds"]},
-        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": cores, "kind": "port",
-                         "host_cores": os.cpu_count(),
-                         "sample": f"oracle/harmony_oracle.py (NumPy, fp32) on the first {n_sample} cells; "
-                                   "init assignment + harmonize to convergence; BLAS threads tuned over {1,8,32,all}"},
-        "e2e": {"value": val, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": workload_config(w, world, N_total),
+        "cpu_baseline": {"value": val, "unit": "cells/s", "cores": r["cores"], "kind": r["kind"],
+                         "host_cores": os.cpu_count(), "sample": r["sample"]},
+        "e2e": {"value": n_sample / float(np.mean(totals)), "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(out), flush=True)
@@ -399,11 +463,9 @@ def run_ours(args, w):
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, dt, info = cpu_oracle_rate(w, Y0, args.cpu_sample)
-        cpu = {"value": rate, "unit": "cells/s", "cores": info.get("threads", os.cpu_count()), "host_cores": os.cpu_count(),
-               "kind": "port", "seconds": dt,
-               "sample": f"oracle/harmony_oracle.py (NumPy fp32 port of harmony.py) on the first {args.cpu_sample} "
-                         f"cells of the workload, init assignment + harmonize to convergence, rounds {info['rounds']}"}
+        r = cpu_arm(w, Y0, args.cpu_sample)
+        cpu = {"value": args.cpu_sample / r["loop_seconds"], "unit": "cells/s", "cores": r["cores"], "host_cores": os.cpu_count(),
+               "kind": r["kind"], "seconds": r["loop_seconds"], "sample": r["sample"]}
 
     parity = None
     if rank == 0 and not args.no_parity:
@@ -413,15 +475,14 @@ def run_ours(args, w):
             "metric": "cells/sec to convergence (full Harmony loop)", "value": value, "unit": "cells/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["name"], "cells_total": N_total, "cells_per_gpu": w["per_gpu"], "d": w["d"],
-                       "levels": w["levels"], "K": w["K"], "parallelism": f"cells sharded over {world} GPU(s)",
-                       "perm_mode": "device", "l2": "inputs larger than L2 (R 400 MB + Z 600 MB per GPU), no flush",
-                       "init": f"sklearn k-means++ on a {min(N_total, INIT_SUBSAMPLE)}-cell subsample, untimed",
-                       "iterations_per_step": tot_iters / args.steps, "rounds_per_step": tot_rounds / args.steps,
-                       "mode": ("persistent round kernel with in-kernel NVLink exchange of the K x B tables (fused, exact)"
-                                if eng.counter("fused") == 1 else
-                                "staged launches + NCCL all-reduce of the K x B tables per block (exact multi-GPU mode)" if world > 1
-                                else "staged launches" if args.staged else "persistent round kernel")},
+            "config": workload_config(w, world, N_total),
+            "run": {"iterations_per_step": tot_iters / args.steps, "rounds_per_step": tot_rounds / args.steps,
+                    "mode": ("persistent round kernel with in-kernel NVLink exchange of the K x B tables (fused, exact)"
+                             if eng.counter("fused") == 1 else
+                             "staged launches + NCCL all-reduce of the K x B tables per block (exact multi-GPU mode)" if world > 1
+                             else "staged launches" if args.staged else
+                             "persistent tcgen05 round kernel (k_round_tc5), one round ahead" if eng.counter("tc5") == 1
+                             else "persistent round kernel")},
             "cell_rounds_per_s": n_local * world * n_rounds / (ms_round / 1e3) if ms_round > 0 else None,
             "ridge_passes_per_s": n_local * world * n_ridge / (ms_ridge / 1e3) if ms_ridge > 0 else None,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "parity": parity, "gpu_launches": int(launches),

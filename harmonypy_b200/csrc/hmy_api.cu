@@ -46,7 +46,8 @@ struct hmy_ctx {
     bool tc5_ok = false;                    // shape supported (decided in plan_round)
     bool t5_state = false;                  // the device tables (running O, removed sums) were produced by that kernel
     int tc5_nc = 0, smem_tc5 = 0, G_tc5 = 0;
-    const void* fn_tc5 = nullptr;
+    const void* fn_tc5 = nullptr; const void* fn_tc5_multi = nullptr;
+    unsigned int x5_seq = 0;                // LL sequence number of the last multi-GPU launch of that kernel
     unsigned char* blkbuf[2] = {nullptr, nullptr};      // block of every cell: round r in blkbuf[r & 1]
     float* t5_told[2] = {nullptr, nullptr}; int told_cur = 0;     // [nblk][B][K] removed sums | [nblk][K] their row sums
     float* t5_dnew = nullptr;                                      // [nblk][B][K] re-added sums | [nblk][K] row sums
@@ -329,9 +330,10 @@ static int plan_round(hmy_ctx* ctx) {
         if (shape) {
             const void* f[2] = {nullptr, nullptr};
             if (st.K <= 64) { hmy_bind_tc5_4(f); ctx->tc5_nc = 4; } else if (st.K <= 112) { hmy_bind_tc5_7(f); ctx->tc5_nc = 7; } else { hmy_bind_tc5_8(f); ctx->tc5_nc = 8; }
-            ctx->fn_tc5 = f[0];
+            ctx->fn_tc5 = f[0]; ctx->fn_tc5_multi = f[1];
             ctx->smem_tc5 = t5_smem_bytes(ctx->tc5_nc);
             CK(cudaFuncSetAttribute(ctx->fn_tc5, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
+            CK(cudaFuncSetAttribute(ctx->fn_tc5_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_tc5));
             int nt5 = 0;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nt5, ctx->fn_tc5, T5_THREADS, ctx->smem_tc5));
             if (nt5 < 1) FAIL("tensor-memory round kernel does not fit on an SM");
@@ -394,10 +396,50 @@ extern "C" int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* thet
     std::vector<float> l(st.B + 1, 0.f);
     if (!lambda_estimation) { if (!lamb) FAIL("lamb is NULL"); std::copy(lamb, lamb + st.B + 1, l.begin()); }
     CK(cudaMemcpy(st.lamb, l.data(), (st.B + 1) * sizeof(float), cudaMemcpyHostToDevice));
+    st.sigma_uniform = 1; st.sigma_u = sigma[0];
+    for (int k = 1; k < st.K; ++k) if (sigma[k] != sigma[0]) st.sigma_uniform = 0;
     st.lambda_estimation = lambda_estimation ? 1 : 0;
     st.alpha = alpha;
     if (plan_round(ctx)) return 1;
     ctx->have_params = true;
+    return 0;
+}
+
+// ---- host-side helpers of the upload / download paths ------------------------------------------------------------
+static int host_threads() { const unsigned hc = std::thread::hardware_concurrency(); return (int)std::max(1u, std::min(16u, hc ? hc : 4u)); }
+
+// fn(t, lo, hi) over [0, n) split into contiguous ranges, one per thread (range t precedes range t + 1)
+template <class F>
+static void parallel_ranges(long long n, int T, F fn) {
+    if (T <= 1 || n < 65536) { fn(0, 0LL, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back([=]() { fn(t, n * t / T, n * (t + 1) / T); });
+    for (auto& x : th) x.join();
+}
+
+static int ensure_stage(hmy_ctx* ctx) {
+    constexpr size_t CHUNK = 16u << 20;
+    if (!ctx->h_stage[0])
+        for (int i = 0; i < 2; ++i) { CK(cudaMallocHost((void**)&ctx->h_stage[i], CHUNK)); CK(cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming)); }
+    return 0;
+}
+
+// pageable host memory -> device through the two pinned bounce buffers: the host copy of chunk i + 1 (spread over
+// threads) overlaps the DMA of chunk i (a plain cudaMemcpy from pageable memory stages single-threaded inside the driver)
+static int h2d_staged(hmy_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    constexpr size_t CHUNK = 16u << 20;
+    if (ensure_stage(ctx)) return 1;
+    const unsigned char* src8 = (const unsigned char*)src_host; unsigned char* dst8 = (unsigned char*)dst_dev;
+    const size_t nchunk = (bytes + CHUNK - 1) / CHUNK;
+    const int T = host_threads();
+    for (size_t i = 0; i < nchunk; ++i) {
+        const size_t off = i * CHUNK, len = std::min(CHUNK, bytes - off);
+        CK(cudaEventSynchronize(ctx->ev_stage[i & 1]));          // the DMA that last used this buffer (this call or an earlier one) is done
+        unsigned char* hb = ctx->h_stage[i & 1];
+        parallel_ranges((long long)len, len >= (2u << 20) ? T : 1, [&](int, long long lo, long long hi) { std::memcpy(hb + lo, src8 + off + lo, (size_t)(hi - lo)); });
+        CK(cudaMemcpyAsync(dst8 + off, hb, len, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_stage[i & 1], ctx->stream));
+    }
     return 0;
 }
 
@@ -414,96 +456,130 @@ extern "C" int hmy_set_data(hmy_ctx* ctx, const float* Z_host, const int32_t* co
     };
     if (!Z_host || !codes_host) FAIL("hmy_set_data: NULL input");
     const long long N = st.N; const int V = st.V;
+    const int T = host_threads();
+    // the big upload first: it streams through the pinned buffers while the host builds the layout below.
+    // R (N x Kp floats, not valid before the init assignment) is the landing area of the raw rows.
+    // Landing area of the raw rows: a buffer that is not valid yet and at least N x d floats large -- R (N x Kp) or the
+    // pre-split operand rows (N x 64 ceil(d / 16) bytes >= 4 d); a temporary allocation only when neither fits.
+    float* raw = nullptr; float* raw_tmp = nullptr;
+    if (st.Kp >= st.d) raw = st.R;
+    else if (st.Zs16) raw = reinterpret_cast<float*>(st.Zs16);
+    else { CK(cudaMalloc((void**)&raw_tmp, (size_t)N * st.d * sizeof(float))); raw = raw_tmp; }
     // combination key of every cell (covariate 0 most significant)
-    std::vector<unsigned long long> key((size_t)N);
+    std::vector<unsigned long long> mult(V, 1ull);
     {
-        std::vector<unsigned long long> mult(V, 1ull);
         long double span = 1.0L;
         for (int v = V - 1; v >= 0; --v) { mult[v] = (unsigned long long)span; span *= ctx->levels[v]; }
         if (span > 9.0e18L) FAIL("product of covariate level counts overflows 64 bits");
-        for (long long n = 0; n < N; ++n) {
+    }
+    std::vector<unsigned long long> key((size_t)N);
+    std::vector<unsigned long long> tmax((size_t)T, 0ull);
+    std::vector<int> bad((size_t)T, 0);
+    parallel_ranges(N, T, [&](int t, long long lo, long long hi) {
+        unsigned long long m = 0; int b = 0;
+        for (long long n = lo; n < hi; ++n) {
             unsigned long long k = 0;
             for (int v = 0; v < V; ++v) {
                 const int c = codes_host[(size_t)v * N + n];
-                if (c < 0 || c >= ctx->levels[v]) FAIL("level code out of range");
+                if (c < 0 || c >= ctx->levels[v]) { b = 1; continue; }
                 k += (unsigned long long)c * mult[v];
             }
-            key[n] = k;
+            key[n] = k; m = std::max(m, k);
         }
-    }
-    // stable sort of the cells by combination key: counting sort when the key range is small
-    // (the usual case: a handful of batch covariates), comparison sort otherwise
+        tmax[t] = m; bad[t] = b;
+    });
+    for (int t = 0; t < T; ++t) if (bad[t]) FAIL("level code out of range");
+    const unsigned long long kmax = *std::max_element(tmax.begin(), tmax.end());
+    // stable sort of the cells by combination key: parallel counting sort when the key range is small (the usual case:
+    // a handful of batch covariates), comparison sort otherwise
     std::vector<int> order((size_t)N);
-    {
-        unsigned long long kmax = 0;
-        for (long long n = 0; n < N; ++n) kmax = std::max(kmax, key[n]);
-        if (kmax < (1ull << 22)) {
-            std::vector<long long> cnt((size_t)kmax + 2, 0);
-            for (long long n = 0; n < N; ++n) cnt[key[n] + 1]++;
-            for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
-            for (long long n = 0; n < N; ++n) order[(size_t)cnt[key[n]]++] = (int)n;
-        } else {
-            std::iota(order.begin(), order.end(), 0);
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-        }
+    if (kmax < (1ull << 16)) {
+        const size_t nk = (size_t)kmax + 1;
+        std::vector<long long> cnt((size_t)T * nk, 0);
+        parallel_ranges(N, T, [&](int t, long long lo, long long hi) { long long* c = &cnt[(size_t)t * nk]; for (long long n = lo; n < hi; ++n) c[key[n]]++; });
+        long long run = 0;                                             // exclusive scan in (key, thread) order: stable
+        for (size_t k = 0; k < nk; ++k) for (int t = 0; t < T; ++t) { const long long c = cnt[(size_t)t * nk + k]; cnt[(size_t)t * nk + k] = run; run += c; }
+        parallel_ranges(N, T, [&](int t, long long lo, long long hi) { long long* c = &cnt[(size_t)t * nk]; for (long long n = lo; n < hi; ++n) order[(size_t)c[key[n]]++] = (int)n; });
+    } else if (kmax < (1ull << 22)) {
+        std::vector<long long> cnt((size_t)kmax + 2, 0);
+        for (long long n = 0; n < N; ++n) cnt[key[n] + 1]++;
+        for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+        for (long long n = 0; n < N; ++n) order[(size_t)cnt[key[n]]++] = (int)n;
+    } else {
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
     }
     lap("keys + counting sort");
+    if (h2d_staged(ctx, raw, Z_host, (size_t)N * st.d * sizeof(float))) return 1;
+    lap("H2D of Z (staged, async)");
+    // combination id of every stored position: boundaries where the key changes, then a prefix count
     std::vector<int> pos_of((size_t)N), combo((size_t)N), combo_lev;
     std::vector<long long> combo_start;
-    int ncombo = 0;
-    for (long long p = 0; p < N; ++p) {
-        const int src = order[p];
-        pos_of[src] = (int)p;
-        if (p == 0 || key[src] != key[order[p - 1]]) {
-            combo_start.push_back(p);
-            for (int v = 0; v < V; ++v) combo_lev.push_back(ctx->level_off[v] + codes_host[(size_t)v * N + src]);
-            ++ncombo;
-        }
-        combo[p] = ncombo - 1;
+    {
+        std::vector<int> nb((size_t)T + 1, 0);
+        parallel_ranges(N, T, [&](int t, long long lo, long long hi) {
+            int c = 0;
+            for (long long p = lo; p < hi; ++p) { pos_of[order[p]] = (int)p; if (p == 0 || key[order[p]] != key[order[p - 1]]) ++c; }
+            nb[t + 1] = c;
+        });
+        for (int t = 0; t < T; ++t) nb[t + 1] += nb[t];
+        const int ncombo = nb[T];
+        combo_start.assign((size_t)ncombo + 1, 0);
+        combo_lev.assign((size_t)ncombo * V, 0);
+        const bool ran_parallel = !(T <= 1 || N < 65536);
+        parallel_ranges(N, T, [&](int t, long long lo, long long hi) {
+            int c = (ran_parallel ? nb[t] : 0) - 1;
+            for (long long p = lo; p < hi; ++p) {
+                const int src = order[p];
+                if (p == 0 || key[src] != key[order[p - 1]]) {
+                    ++c;
+                    combo_start[c] = p;
+                    for (int v = 0; v < V; ++v) combo_lev[(size_t)c * V + v] = ctx->level_off[v] + codes_host[(size_t)v * N + src];
+                }
+                combo[p] = c;
+            }
+        });
+        combo_start[ncombo] = N;
+        st.ncombo = ncombo;
     }
-    combo_start.push_back(N);
-    st.ncombo = ncombo;
+    const int ncombo = st.ncombo;
     lap("pos_of / combo tables");
     // ridge work items: <= HMY_SEG_MAX consecutive cells of one combination
     std::vector<int> seg;
     for (int c = 0; c < ncombo; ++c)
-        for (long long s = combo_start[c]; s < combo_start[c + 1]; s += HMY_SEG_MAX) {
-            seg.push_back((int)s); seg.push_back((int)std::min<long long>(HMY_SEG_MAX, combo_start[c + 1] - s)); seg.push_back(c);
+        for (long long s0 = combo_start[c]; s0 < combo_start[c + 1]; s0 += HMY_SEG_MAX) {
+            seg.push_back((int)s0); seg.push_back((int)std::min<long long>(HMY_SEG_MAX, combo_start[c + 1] - s0)); seg.push_back(c);
         }
     st.nseg = (int)(seg.size() / 3);
     if (dev_alloc(ctx, &st.combo_lev, combo_lev.size())) return 1;
     if (dev_alloc(ctx, &st.combo_start, combo_start.size())) return 1;
     if (dev_alloc(ctx, &st.seg, seg.size())) return 1;
-    CK(cudaMemcpy(st.combo_lev, combo_lev.data(), combo_lev.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(st.combo_start, combo_start.data(), combo_start.size() * sizeof(long long), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(st.seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(st.combo, combo.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(st.order, order.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(st.pos_of, pos_of.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-    lap("small uploads");
-    lap("max |Z|");
+    CK(cudaMemcpyAsync(st.combo_lev, combo_lev.data(), combo_lev.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(st.combo_start, combo_start.data(), combo_start.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(st.seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    if (h2d_staged(ctx, st.combo, combo.data(), (size_t)N * sizeof(int))) return 1;
+    if (h2d_staged(ctx, st.order, order.data(), (size_t)N * sizeof(int))) return 1;
+    if (h2d_staged(ctx, st.pos_of, pos_of.data(), (size_t)N * sizeof(int))) return 1;
+    lap("small uploads (async)");
     // raw rows -> sorted padded layout + Z_cos
-    float* raw = nullptr;
-    CK(cudaMalloc((void**)&raw, (size_t)N * st.d * sizeof(float)));
-    cudaError_t e = cudaMemcpyAsync(raw, Z_host, (size_t)N * st.d * sizeof(float), cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) {
+    {
         const long long threads = N * 32;
-        cudaMemsetAsync(st.wmax, 0, sizeof(float), ctx->stream);        // borrowed as the |z| maximum
+        CK(cudaMemsetAsync(st.wmax, 0, sizeof(float), ctx->stream));        // borrowed as the |z| maximum
         k_ingest<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(st, raw, st.wmax);
         ctx->launches++;
-        e = cudaGetLastError();
+        CK(cudaGetLastError());
     }
+    if (split_zcos(ctx)) return 1;
     float zm = 0.f;
-    if (e == cudaSuccess) e = cudaMemcpyAsync(&zm, st.wmax, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    CK(cudaMemcpyAsync(&zm, st.wmax, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));          // also: the host vectors above may go out of scope now
+    if (raw_tmp) cudaFree(raw_tmp);
     {   // scale of the fp16 split of Z_orig in the tensor-core ridge passes: hi part below 2^14
         int ex = 0; std::frexp(std::max(zm, 1e-30f), &ex);
         ctx->zscale = std::ldexp(1.0f, 13 - ex);
     }
-    cudaFree(raw);
-    CK(e);
-    if (split_zcos(ctx)) return 1;
-    lap("malloc + H2D + ingest + free");
+    ctx->r_valid = false;                            // R served as the landing area of the upload
+    lap("ingest + sync");
     ctx->have_data = true;
     return 0;
 }
@@ -580,7 +656,11 @@ static int launch_persistent(hmy_ctx* ctx, void** args) {
 // ---- tensor-memory round kernel: host side ----------------------------------------------------------------------
 // It is the path of single-GPU persistent runs whose shape it supports; sharded runs (all-reduce callback or
 // peer exchange) and launch-per-block mode stay on the mma.sync / SIMT kernels.
-static inline bool use_tc5(const hmy_ctx* ctx) { return ctx->tc5_ok && ctx->persistent && !ctx->ar && !ctx->fused; }
+static inline bool use_tc5(const hmy_ctx* ctx) {
+    // sharded runs: with the peer exchange attached (fused) and exact per-block exchange only; the staged all-reduce
+    // mode and the "relaxed" one-exchange-per-round variant stay on the mma.sync kernel
+    return ctx->tc5_ok && ctx->persistent && (!ctx->ar || ctx->fused) && !(ctx->fused && ctx->st.xrelaxed);
+}
 
 static int split_zcos(hmy_ctx* ctx) {
     HmyDev& st = ctx->st;
@@ -631,7 +711,8 @@ static int launch_tc5(hmy_ctx* ctx, int mode) {
     else { s.blk = ctx->blkbuf[r & 1]; s.blk_next = ctx->blkbuf[(r + 1) & 1]; }
     unsigned long long base = ctx->bar_count64;
     void* args[] = {&s, &mode, &base};
-    if (launch(ctx, ctx->fn_tc5, dim3(ctx->G_tc5), dim3(T5_THREADS), args, ctx->smem_tc5, true)) return 1;
+    if (ctx->fused) s.x5_seq = ++ctx->x5_seq;
+    if (launch(ctx, ctx->fused ? ctx->fn_tc5_multi : ctx->fn_tc5, dim3(ctx->G_tc5), dim3(T5_THREADS), args, ctx->smem_tc5, true)) return 1;
     ctx->bar_count64 += (unsigned long long)ctx->G_tc5 * (unsigned long long)(mode == 1 ? 1 : s.nblk);
     ctx->r_valid = ctx->write_r != 0;
     ctx->t5_state = true;
@@ -640,9 +721,17 @@ static int launch_tc5(hmy_ctx* ctx, int mode) {
 
 // objective sums of the last tc5 stage: the kernel leaves them in obj[0..2]
 static int fetch_obj_tc5(hmy_ctx* ctx, double obj[3]) {
-    CK(cudaMemcpyAsync(ctx->h_obj, ctx->st.obj, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_obj, ctx->st.obj, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double go[2] = {0.0, 0.0};
+    if (ctx->fused) CK(cudaMemcpyAsync(go, ctx->st.obj_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (obj) { obj[0] = ctx->h_obj[0]; obj[1] = ctx->h_obj[1]; obj[2] = ctx->h_obj[2]; }
+    if (obj) {
+        if (ctx->fused) {
+            // sums over all ranks (rank order) and the cross-entropy term in 2^-30 fixed point: identical on every rank
+            long long fx; std::memcpy(&fx, &ctx->h_obj[3], sizeof fx);
+            obj[0] = go[0]; obj[1] = go[1]; obj[2] = (double)fx / 1073741824.0;
+        } else { obj[0] = ctx->h_obj[0]; obj[1] = ctx->h_obj[1]; obj[2] = ctx->h_obj[2]; }
+    }
     return 0;
 }
 
@@ -919,9 +1008,7 @@ static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_o
     // device -> pinned bounce buffer -> caller's (pageable, usually untouched) array, double buffered:
     // the DMA of chunk i+1 overlaps the host copy (and first-touch page faults) of chunk i
     constexpr size_t CHUNK = 16u << 20;
-    if (!ctx->h_stage[0]) {
-        for (int i = 0; i < 2; ++i) { CK(cudaMallocHost((void**)&ctx->h_stage[i], CHUNK)); CK(cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming)); }
-    }
+    if (ensure_stage(ctx)) return 1;
     const unsigned char* src8 = reinterpret_cast<const unsigned char*>(ctx->d_tmp);
     unsigned char* dst8 = reinterpret_cast<unsigned char*>(host_out);
     const size_t nchunk = (need + CHUNK - 1) / CHUNK;
@@ -936,18 +1023,9 @@ static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_o
             CK(cudaEventSynchronize(ctx->ev_stage[j & 1]));
             // the destination is usually a fresh (never touched) array: its first-touch page faults
             // dominate, so the copy is spread over a few host threads
-            const int nthr = (len >= (4u << 20)) ? 4 : 1;
-            if (nthr == 1) {
-                std::memcpy(dst8 + off, ctx->h_stage[j & 1], len);
-            } else {
-                std::thread th[4];
-                const size_t part = ((len / nthr) + 4095) & ~(size_t)4095;
-                for (int t = 0; t < nthr; ++t) {
-                    const size_t o2 = std::min(len, (size_t)t * part), l2 = std::min(part, len - o2);
-                    th[t] = std::thread([=]() { if (l2) std::memcpy(dst8 + off + o2, ctx->h_stage[j & 1] + o2, l2); });
-                }
-                for (int t = 0; t < nthr; ++t) th[t].join();
-            }
+            const unsigned char* hb = ctx->h_stage[j & 1];
+            parallel_ranges((long long)len, len >= (2u << 20) ? host_threads() : 1,
+                            [&](int, long long lo, long long hi) { std::memcpy(dst8 + off + lo, hb + lo, (size_t)(hi - lo)); });
         }
     }
     return 0;
@@ -1059,6 +1137,7 @@ extern "C" int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value) {
         ctx->want_tc5 = (int)value; return 0;
     }
     if (n == "write_r") { ctx->write_r = value != 0; return 0; }
+    if (n == "dbg") { ctx->st.dbg = (int)value; return 0; }          // timing experiments (wrong results); see hmy_round_tc5.cuh
     if (n == "reset") {
         // back to the freshly-uploaded state (benchmark steps restart from here)
         CK(cudaSetDevice(ctx->device));
@@ -1116,7 +1195,7 @@ extern "C" int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B) {
     HmyDev& st = ctx->st;
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_params) FAIL("hmy_comm_export: call hmy_set_params first");
-    if (!ctx->use_mma) FAIL("hmy_comm_export: the fused exchange needs the tensor-core round kernel (d <= 64)");
+    if (!ctx->use_mma && !ctx->tc5_ok) FAIL("hmy_comm_export: the fused exchange needs a tensor-core round kernel (d <= 64)");
     if (!handle_out_64B) FAIL("hmy_comm_export: NULL handle");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     if (!ctx->xbuf) {
@@ -1127,6 +1206,15 @@ extern "C" int hmy_comm_export(hmy_ctx* ctx, void* handle_out_64B) {
         st.xll_count = st.B * st.K;
         ctx->xbytes = HMY_XPAYLOAD_OFF + 2 * (size_t)HMY_MAX_WORLD * slot
                     + 2 * (size_t)HMY_MAX_WORLD * (size_t)st.xll_count * sizeof(uint2);
+        if (ctx->tc5_ok) {
+            // LL regions of the tensor-memory round kernel (hmy_round_tc5.cuh): per-block sums [2][nblk][W][nD], the next
+            // round's removed sums [2][W][nblk nD], centroid / objective sums as double halves [2][W][2 (K dp + 2)]
+            const size_t nD = (size_t)st.B * st.K + st.K, nT = (size_t)st.nblk * nD, nY = (size_t)st.K * st.dp + 2;
+            ctx->xbytes = (ctx->xbytes + 255) & ~(size_t)255;
+            st.x5_off_d = ctx->xbytes; ctx->xbytes += 2 * nT * HMY_MAX_WORLD * sizeof(uint2);
+            st.x5_off_t = ctx->xbytes; ctx->xbytes += 2 * (size_t)HMY_MAX_WORLD * nT * sizeof(uint2);
+            st.x5_off_y = ctx->xbytes; ctx->xbytes += 2 * (size_t)HMY_MAX_WORLD * 2 * nY * sizeof(uint2);
+        }
         CK(cudaMalloc((void**)&ctx->xbuf, ctx->xbytes));
         CK(cudaMemset(ctx->xbuf, 0, ctx->xbytes));
     }

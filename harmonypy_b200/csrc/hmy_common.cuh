@@ -21,7 +21,7 @@
 #define HMY_CPW 8            // cells per warp inside a tile (HMY_TILE / HMY_WARPS)
 #define HMY_MAX_V 8
 #define HMY_MAX_NBLK 250
-#define HMY_TRACE_SLOTS 128
+#define HMY_TRACE_SLOTS 192
 #define HMY_MAX_WORLD 8
 #define HMY_XFLAG_STRIDE 128     // bytes between the per-source flags of an exchange buffer
 #define HMY_XPAYLOAD_OFF 4096
@@ -76,10 +76,23 @@ struct HmyDev {
     double* Rsum; double* Rsum_next; // [K] running sum_n R[n][k] of this round / start value of the next one
     unsigned long long* bar64;       // monotone grid-barrier counter
     int write_R;                     // 1: the round stores the new R rows to HBM
+    unsigned long long x5_off_d, x5_off_t, x5_off_y;   // byte offsets of the LL regions of that kernel in every rank's exchange buffer
+    unsigned int x5_seq;             // sequence number of this launch (LL packets carry it)
+    int dbg;                         // timing experiments only (option "dbg", results are WRONG when set): see hmy_round_tc5.cuh
+    int sigma_uniform; float sigma_u;   // every cluster has the same sigma (the usual case): no per-cluster constants to load
 };
 
 __device__ __forceinline__ void hmy_trace(const HmyDev& st, int slot) {
     if (st.trace != nullptr && threadIdx.x == 0 && slot < HMY_TRACE_SLOTS) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + slot] = t;
+    }
+}
+
+// the same from any single thread (warp-specialised kernels: the issuing thread of a role)
+__device__ __forceinline__ void hmy_trace_any(const HmyDev& st, int slot) {
+    if (st.trace != nullptr && slot < HMY_TRACE_SLOTS) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + slot] = t;

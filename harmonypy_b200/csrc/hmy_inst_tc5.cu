@@ -12,6 +12,6 @@
 #define HMY_CATT(a) HMY_CATT2(a)
 
 extern "C" void HMY_CATT(HMY_TC5_NC)(const void** fns) {
-    fns[0] = (const void*)k_round_tc5<HMY_TC5_NC>;
-    fns[1] = nullptr;
+    fns[0] = (const void*)k_round_tc5<HMY_TC5_NC, false>;
+    fns[1] = (const void*)k_round_tc5<HMY_TC5_NC, true>;
 }

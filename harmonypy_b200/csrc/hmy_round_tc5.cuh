@@ -43,8 +43,8 @@
 // tensor-memory columns (512 allocated)
 #define T5_COL_D1 0              // + 128 * buffer
 #define T5_COL_Y 256
-#define T5_COL_O 320             // + 16 * slot (every column of a slot holds the same sum)
-#define T5_COL_T 384             // + 32 * slot + next block
+#define T5_COL_OT 320            // + 48 * slot: 16 columns that all hold the slot's column sums of R, then 32 columns
+                                 // of those sums split by the cell's block in the next round (one MMA pair feeds both)
 // shared memory (dynamic, 1024-byte aligned)
 #define T5_SZ_ZPART 16384
 #define T5_SZ_STAGE 32768
@@ -52,9 +52,9 @@
 #define T5_OFF_Z 0
 #define T5_OFF_RH (T5_NZ * T5_SZ_STAGE)
 #define T5_OFF_RL (T5_OFF_RH + T5_SZ_RPART)
-#define T5_OFF_NB (T5_OFF_RL + T5_SZ_RPART)          // one-hot(next block): 32 columns x 128 cells
-#define T5_OFF_ONES (T5_OFF_NB + 8192)                // 16 columns x 16 cells of 1.0
-#define T5_OFF_YH (T5_OFF_ONES + 512)
+#define T5_OFF_NB (T5_OFF_RL + T5_SZ_RPART)          // MN-major B tile of 48 columns x 128 cells: 16 columns of 1.0 (written once),
+#define T5_SZ_NB (6 * 2048)                           // then one-hot(block of the cell in the next round)
+#define T5_OFF_YH (T5_OFF_NB + T5_SZ_NB)
 __host__ __device__ constexpr int t5_off_yl(int NC) { return T5_OFF_YH + NC * 2048; }
 __host__ __device__ constexpr int t5_off_ps(int NC) { return t5_off_yl(NC) + NC * 2048; }      // float2 [4][KT2] {pen, sigma ln pen}
 __host__ __device__ constexpr int t5_off_ck(int NC) { return t5_off_ps(NC) + T5_SLOTS * 16 * NC * 8; }   // float2 [KT2] {-log2e / sigma, sigma}
@@ -114,9 +114,18 @@ __device__ __forceinline__ void t5_commit(unsigned int bar) {
 __device__ __forceinline__ void t5_arrive(unsigned int bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(bar) : "memory");
 }
+// try_wait may suspend the thread for a system-dependent time before it reports "not yet": right for a thread that
+// waits for ONE barrier (t5_wait), wrong for a role that polls several (it would sit out the time limit on the first
+// one while the second has long completed): t5_poll is the non-blocking test
 __device__ __forceinline__ bool t5_test(unsigned int bar, unsigned int parity) {
     unsigned int done;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done != 0u;
+}
+__device__ __forceinline__ bool t5_poll(unsigned int bar, unsigned int parity) {
+    unsigned int done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
     return done != 0u;
 }
@@ -195,10 +204,13 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
         if (mode == 1) { lb = (long long)blockIdx.x * st.N / G; le = (long long)(blockIdx.x + 1) * st.N / G; }
         else block_share(st, blk, blockIdx.x, G, lb, le);
         long long cur = lb;
+        int pr_in_blk = 0;
         do {
             const unsigned int s = t % T5_NZ, use = t / T5_NZ;
+            const int psl = (blk == 5 && pr_in_blk < 4 && lane == 0) ? 144 + 4 * pr_in_blk : HMY_TRACE_SLOTS;
+            ++pr_in_blk;
             const unsigned int bacc = bar0 + 8u * (T5_B_ACC + s);
-            if (!t5_test(bacc, (use & 1u) ^ 1u)) {
+            if (!t5_poll(bacc, (use & 1u) ^ 1u)) {
                 // the stage is still in use: hand over the previous tile first, then wait
                 if (pending) {
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -209,6 +221,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
                 }
                 t5_wait(bacc, (use & 1u) ^ 1u);
             }
+            hmy_trace_any(st, psl);
             unsigned char* meta = smem + t5_off_meta(NC) + s * 1024;
             int* mcell = reinterpret_cast<int*>(meta);
             unsigned short* mslot = reinterpret_cast<unsigned short*>(meta + T5_META_SLOTNB);
@@ -289,6 +302,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
                 hdr[T5_H_KSLOT] = (int)ks_lo; hdr[T5_H_KSLOT + 1] = (int)ks_hi;
             }
             __syncwarp();
+            hmy_trace_any(st, psl + 1);
             // ---- gather: 8 rows x 4 chunks of 16 bytes per instruction (conflict-free core-matrix writes)
             {
                 const int r8 = lane & 7, cs = lane >> 3;
@@ -307,6 +321,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
+            hmy_trace_any(st, psl + 2);
             if (pending) {
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 t5_fence_async();
@@ -325,95 +340,196 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
     }
 }
 
-// ---- MMA warp (one thread) -------------------------------------------------------------------------------------------
+// ---- MMA warp -----------------------------------------------------------------------------------------------------
+// The whole warp runs the loop with uniform control flow and one elected lane issues (a tcgen05.mma in divergent
+// code is wrapped in a per-instruction election loop by the compiler; at N <= 64 that issue overhead, not the tensor
+// pipe, set the pace: experiments/tcgen05_mma_rate.cu).  Everything the loop reads from shared memory passes through
+// a warp reduction so that the compiler knows it is warp-uniform (descriptor arithmetic on the uniform datapath).
+__device__ __forceinline__ bool t5_elect() {
+    unsigned int pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}\n" : "=r"(pred));
+    return pred != 0u;
+}
+__device__ __forceinline__ unsigned int t5_uni(unsigned int x) { return __reduce_or_sync(0xffffffffu, x); }
+
 template <int NC>
-__device__ void t5_mma_thread(const HmyDev& st, unsigned char* smem, unsigned int bar0, unsigned int tmem) {
+__device__ void t5_mma_warp(const HmyDev& st, unsigned char* smem, unsigned int bar0, unsigned int tmem) {
+    const int lane = threadIdx.x & 31;
     const int dt = (st.d + 15) >> 4;
     const unsigned int sb = smem_u32(smem);
-    const unsigned int id_score = t5_idesc(T5_TILE, 16 * NC, 0, 0), id_y = t5_idesc(128, 16 * dt, 1, 1);
-    const unsigned int id_o = t5_idesc(128, 16, 1, 1), id_t = t5_idesc(128, 32, 1, 1);
+    const unsigned int id_score = t5_idesc(T5_TILE, 16 * NC, 0, 0), id_y = t5_idesc(128, 16 * dt, 1, 1), id_ot = t5_idesc(128, 48, 1, 1);
     const unsigned long long dYh = t5_desc(sb + T5_OFF_YH, T5_LBO_K, T5_SBO_K), dYl = t5_desc(sb + t5_off_yl(NC), T5_LBO_K, T5_SBO_K);
     const unsigned long long dRh = t5_desc(sb + T5_OFF_RH, T5_R_LBO, T5_R_SBO), dRl = t5_desc(sb + T5_OFF_RL, T5_R_LBO, T5_R_SBO);
-    const unsigned long long dOnes = t5_desc(sb + T5_OFF_ONES, 128, 256);
     const unsigned long long dNb = t5_desc(sb + T5_OFF_NB, T5_R_LBO, T5_R_SBO);
+    const unsigned long long dZK = t5_desc(sb + T5_OFF_Z, T5_LBO_K, T5_SBO_K);            // stage 0, hi part, K-major view
+    const unsigned long long dZM = t5_desc(sb + T5_OFF_Z, T5_Z_LBO_MN, T5_Z_SBO_MN);      // the same bytes MN-major
+    constexpr unsigned long long STAGE16 = T5_SZ_STAGE >> 4, PART16 = T5_SZ_ZPART >> 4;
     unsigned int ts = 0, ta = 0;                       // next tile to score / to accumulate
     bool score_end = false, y_started = false;
-    unsigned int o_started = 0u, t_started = 0u;       // per-slot: accumulator holds sums
+    unsigned int ot_started = 0u;                      // per slot: its accumulator columns hold sums
     unsigned int idle = 0; unsigned long long idle_t0 = 0;
+    int sc_in_blk = 0, ac_in_blk = 0;                  // timeline (option "trace"): tiles of block 5, slots 128 + 4 i + {0..3}
     for (;;) {
         bool progressed = false;
         if (!score_end) {
             const unsigned int s = ts % T5_NZ, d = ts & 1u;
-            if (t5_test(bar0 + 8u * (T5_B_ZFULL + s), (ts / T5_NZ) & 1u) && t5_test(bar0 + 8u * (T5_B_SFREE + d), ((ts >> 1) & 1u) ^ 1u)) {
+            const bool ready = t5_poll(bar0 + 8u * (T5_B_ZFULL + s), (ts / T5_NZ) & 1u) && t5_poll(bar0 + 8u * (T5_B_SFREE + d), ((ts >> 1) & 1u) ^ 1u);
+            if (__all_sync(0xffffffffu, ready)) {
                 t5_fence_after();
                 const int* hdr = reinterpret_cast<const int*>(smem + t5_off_meta(NC) + s * 1024 + T5_META_HDR);
-                const unsigned int flags = (unsigned int)hdr[T5_H_FLAGS];
-                if (!(flags & T5_F_EMPTY)) {
-                    const unsigned int zh = sb + T5_OFF_Z + s * T5_SZ_STAGE, zl = zh + T5_SZ_ZPART;
-                    const unsigned long long dZh = t5_desc(zh, T5_LBO_K, T5_SBO_K), dZl = t5_desc(zl, T5_LBO_K, T5_SBO_K);
-                    for (int ks = 0; ks < dt; ++ks) {
-                        const unsigned long long o = (unsigned long long)((ks * 2 * T5_LBO_K) >> 4);
-                        t5_mma(tmem + T5_COL_D1 + 128u * d, dZl + o, dYh + o, id_score, ks > 0 ? 1u : 0u);
-                        t5_mma(tmem + T5_COL_D1 + 128u * d, dZh + o, dYl + o, id_score, 1u);
-                        t5_mma(tmem + T5_COL_D1 + 128u * d, dZh + o, dYh + o, id_score, 1u);
+                const unsigned int flags_v = (unsigned int)hdr[T5_H_FLAGS];
+                const bool f_empty = __any_sync(0xffffffffu, (flags_v & T5_F_EMPTY) != 0u);
+                const bool f_lastb = __any_sync(0xffffffffu, (flags_v & T5_F_LAST_BLOCK) != 0u);
+                const bool f_lastr = __any_sync(0xffffffffu, (flags_v & T5_F_LAST_ROUND) != 0u);
+                const int tsl = (hdr[T5_H_BLK] == 5 && sc_in_blk < 4 && lane == 0) ? 128 + 4 * sc_in_blk : HMY_TRACE_SLOTS;
+                hmy_trace_any(st, tsl);
+                if (!f_empty) {
+                    const unsigned long long dZh = dZK + (unsigned long long)s * STAGE16, dZl = dZh + PART16;
+                    const unsigned int dcol = tmem + T5_COL_D1 + 128u * d;
+                    // straight-line code on purpose (here and below): this warp shares its instruction cache with four
+                    // epilogue warps that stream through far more code than it holds -- a loop's backward branch
+                    // refetches its lines every iteration (measured: ~190 cycles per iteration of an EMPTY loop)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        if (ks < dt) {
+                            const unsigned long long o = (unsigned long long)((ks * 2 * T5_LBO_K) >> 4);
+                            if (t5_elect()) {
+                                t5_mma(dcol, dZl + o, dYh + o, id_score, ks > 0 ? 1u : 0u);
+                                t5_mma(dcol, dZh + o, dYl + o, id_score, 1u);
+                                t5_mma(dcol, dZh + o, dYh + o, id_score, 1u);
+                            }
+                        }
                     }
                 }
-                t5_commit(bar0 + 8u * (T5_B_SFULL + d));
-                if (flags & T5_F_LAST_ROUND) score_end = true;
+                if (t5_elect()) t5_commit(bar0 + 8u * (T5_B_SFULL + d));
+                hmy_trace_any(st, tsl + 1);
+                sc_in_blk = f_lastb ? 0 : sc_in_blk + 1;
+                if (f_lastr) score_end = true;
                 ++ts;
                 progressed = true;
             }
         }
-        if (ta < ts && t5_test(bar0 + 8u * T5_B_RFULL, ta & 1u)) {
+        if (ta < ts && __all_sync(0xffffffffu, t5_poll(bar0 + 8u * T5_B_RFULL, ta & 1u))) {
             t5_fence_after();
             const unsigned int s = ta % T5_NZ;
             const int* hdr = reinterpret_cast<const int*>(smem + t5_off_meta(NC) + s * 1024 + T5_META_HDR);
-            const unsigned int flags = (unsigned int)hdr[T5_H_FLAGS];
-            if (flags & T5_F_EVICT) { o_started = 0u; t_started = 0u; }
-            if (!(flags & T5_F_EMPTY)) {
-                const unsigned int kslo = (unsigned int)hdr[T5_H_KSLOT], kshi = (unsigned int)hdr[T5_H_KSLOT + 1];
-                const unsigned int zh = sb + T5_OFF_Z + s * T5_SZ_STAGE, zl = zh + T5_SZ_ZPART;
-                const unsigned long long dZh = t5_desc(zh, T5_Z_LBO_MN, T5_Z_SBO_MN), dZl = t5_desc(zl, T5_Z_LBO_MN, T5_Z_SBO_MN);
-                // the per-slot column sums first: they are what the end of a block waits for
+            // Every decision below goes through a warp vote (a uniform predicate the compiler can branch on without
+            // treating the region as divergent -- a branch on a value loaded from shared memory makes it move every
+            // descriptor into uniform registers again for every MMA: ~15 R2UR per K step, measured 120 cycles per step).
+            const unsigned int flags_v = (unsigned int)hdr[T5_H_FLAGS];
+            const bool f_empty = __any_sync(0xffffffffu, (flags_v & T5_F_EMPTY) != 0u);
+            const bool f_lastb = __any_sync(0xffffffffu, (flags_v & T5_F_LAST_BLOCK) != 0u);
+            const bool f_lastr = __any_sync(0xffffffffu, (flags_v & T5_F_LAST_ROUND) != 0u);
+            const bool f_evict = __any_sync(0xffffffffu, (flags_v & T5_F_EVICT) != 0u);
+            const int blk_v = hdr[T5_H_BLK];
+            const int tsl = (blk_v == 5 && ac_in_blk < 4 && lane == 0) ? 130 + 4 * ac_in_blk : HMY_TRACE_SLOTS;
+            hmy_trace_any(st, tsl);
+            if (f_evict) ot_started = 0u;
+            const bool cyc = st.trace != nullptr && blk_v == 5 && ac_in_blk == 0 && lane == 0;
+#define T5_CYC(i_) do { if (cyc) st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + 160 + (i_)] = (unsigned long long)clock64(); } while (0)
+            T5_CYC(0);
+            const unsigned int kslo = (unsigned int)hdr[T5_H_KSLOT], kshi = (unsigned int)hdr[T5_H_KSLOT + 1];
+            T5_CYC(1);
+            if (!f_empty) {
+                // the per-slot column sums first: they are what the end of a block waits for.  K steps without cells
+                // (slot byte 0xFF) are not issued; their predicate is a vote as well.
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const unsigned int slot = ((ks < 4 ? kslo >> (8 * ks) : kshi >> (8 * (ks - 4))) & 0xFFu);
-                    if (slot == 0xFFu) continue;
+                    const unsigned int sl = ((ks < 4 ? kslo >> (8 * ks) : kshi >> (8 * (ks - 4))) & 0xFFu);
+                    const bool on = __any_sync(0xffffffffu, sl != 0xFFu);
+                    const unsigned int slot = sl & 3u;
                     const unsigned long long ro = (unsigned long long)((ks * 2 * T5_R_LBO) >> 4);
-                    t5_mma(tmem + T5_COL_O + 16u * slot, dRh + ro, dOnes, id_o, (o_started >> slot) & 1u);
-                    t5_mma(tmem + T5_COL_O + 16u * slot, dRl + ro, dOnes, id_o, 1u);
-                    o_started |= 1u << slot;
+                    const unsigned int dcol = tmem + T5_COL_OT + 48u * slot;
+                    if (on && !(st.dbg & 2)) {
+                        if (t5_elect()) {
+                            t5_mma(dcol, dRh + ro, dNb + ro, id_ot, (ot_started >> slot) & 1u);
+                            t5_mma(dcol, dRl + ro, dNb + ro, id_ot, 1u);
+                        }
+                    }
+                    if (on) ot_started |= 1u << slot;
                 }
             }
-            if (flags & T5_F_LAST_BLOCK) t5_commit(bar0 + 8u * T5_B_ODONE);
-            if (!(flags & T5_F_EMPTY)) {
-                const unsigned int kslo = (unsigned int)hdr[T5_H_KSLOT], kshi = (unsigned int)hdr[T5_H_KSLOT + 1];
-                const unsigned int zh = sb + T5_OFF_Z + s * T5_SZ_STAGE, zl = zh + T5_SZ_ZPART;
-                const unsigned long long dZh = t5_desc(zh, T5_Z_LBO_MN, T5_Z_SBO_MN), dZl = t5_desc(zl, T5_Z_LBO_MN, T5_Z_SBO_MN);
+            T5_CYC(2);
+            if (f_lastb) { if (t5_elect()) t5_commit(bar0 + 8u * T5_B_ODONE); }
+            if (!f_empty) {
+                const unsigned long long dZh = dZM + (unsigned long long)s * STAGE16, dZl = dZh + PART16;
+#pragma unroll
                 for (int ks = 0; ks < 8; ++ks) {
-                    const unsigned int slot = ((ks < 4 ? kslo >> (8 * ks) : kshi >> (8 * (ks - 4))) & 0xFFu);
-                    if (slot == 0xFFu) continue;
+                    const unsigned int sl = ((ks < 4 ? kslo >> (8 * ks) : kshi >> (8 * (ks - 4))) & 0xFFu);
+                    const bool on = __any_sync(0xffffffffu, sl != 0xFFu);
                     const unsigned long long ro = (unsigned long long)((ks * 2 * T5_R_LBO) >> 4);
                     const unsigned long long zo = (unsigned long long)((ks * 2 * T5_Z_LBO_MN) >> 4);
-                    t5_mma(tmem + T5_COL_Y, dRl + ro, dZh + zo, id_y, y_started ? 1u : 0u);
-                    t5_mma(tmem + T5_COL_Y, dRh + ro, dZl + zo, id_y, 1u);
-                    t5_mma(tmem + T5_COL_Y, dRh + ro, dZh + zo, id_y, 1u);
-                    y_started = true;
-                    t5_mma(tmem + T5_COL_T + 32u * slot, dRh + ro, dNb + ro, id_t, (t_started >> slot) & 1u);
-                    t5_mma(tmem + T5_COL_T + 32u * slot, dRl + ro, dNb + ro, id_t, 1u);
-                    t_started |= 1u << slot;
+                    if (on && !(st.dbg & 1)) {
+                        if (t5_elect()) {
+                            t5_mma(tmem + T5_COL_Y, dRl + ro, dZh + zo, id_y, y_started ? 1u : 0u);
+                            t5_mma(tmem + T5_COL_Y, dRh + ro, dZl + zo, id_y, 1u);
+                            t5_mma(tmem + T5_COL_Y, dRh + ro, dZh + zo, id_y, 1u);
+                        }
+                    }
+                    if (on) y_started = true;
                 }
             }
-            t5_commit(bar0 + 8u * (T5_B_ACC + s));
-            if (flags & T5_F_LAST_BLOCK) o_started = 0u;
+            T5_CYC(3);
+            if (t5_elect()) t5_commit(bar0 + 8u * (T5_B_ACC + s));
+            T5_CYC(4);
+            hmy_trace_any(st, tsl + 1);
+            T5_CYC(5);
+            ac_in_blk = f_lastb ? 0 : ac_in_blk + 1;
             ++ta;
             progressed = true;
-            if (flags & T5_F_LAST_ROUND) break;
+            if (f_lastr) break;
         }
         if (progressed) { idle = 0; idle_t0 = 0; }
         else if ((++idle & 255u) == 0u) {                 // nothing to issue for seconds: an error, not a hang
             unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
             if (idle_t0 == 0) idle_t0 = tn; else if (tn - idle_t0 > 4000000000ull) __trap();
         }
+    }
+}
+
+// ---- small tables and their cross-GPU form --------------------------------------------------------------------------
+// Per block the round needs two tables of nD = B K + K floats: [level][cluster] sums and, behind them, the per-cluster
+// row sums (every cell has exactly one level of covariate 0, so the row sum of R is a column sum over those levels):
+//   Told[blk]  what block blk takes out of O (accumulated by the PREVIOUS launch, complete and already summed over ranks)
+//   Dnew[blk]  what block blk put back (atomics of this launch; complete on this rank once its barrier has been passed)
+// With the cells sharded over GPUs (MULTI) nothing waits at a cross-GPU barrier: after the rank's own barrier every CTA
+// pushes its slice of Dnew[blk] to every rank as LL packets {value, sequence number of the launch} (8-byte stores are
+// atomic, the reader polls the packet itself) into slot [round parity][blk][source rank] of the peer-mapped exchange
+// buffer, and whoever needs an element sums the W sources in rank order -- identical totals on every rank.  The end of
+// a round moves the next round's Told table, the centroid sums and the objective sums the same way.
+__device__ __forceinline__ size_t t5_nD(const HmyDev& st) { return (size_t)st.B * st.K + st.K; }
+
+__device__ __forceinline__ float t5_ll_read(const uint2* p, unsigned int seq) {
+    uint2 v = ld_volatile_v2(p);
+    unsigned int spins = 0; unsigned long long t0 = 0;
+    while (v.y != seq) {
+        if ((++spins & 1023u) == 0u) {
+            unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t; else if (t - t0 > 8000000000ull) __trap();
+        }
+        v = ld_volatile_v2(p);
+    }
+    return __uint_as_float(v.x);
+}
+// element e of this launch's Dnew[i], summed over ranks
+template <bool MULTI>
+__device__ __forceinline__ float t5_dnew(const HmyDev& st, int i, size_t e) {
+    const size_t nD = t5_nD(st);
+    if (!MULTI) return __ldcg(&st.Dnew[(size_t)i * nD + e]);
+    const uint2* base = reinterpret_cast<const uint2*>(st.xpeer[st.xrank] + st.x5_off_d) + ((size_t)(st.x5_seq & 1u) * st.nblk + i) * HMY_MAX_WORLD * nD + e;
+    float s = 0.f;
+    for (int r = 0; r < st.xworld; ++r) s += t5_ll_read(base + (size_t)r * nD, st.x5_seq);
+    return s;
+}
+// after the rank's barrier: this CTA's slice of Dnew[blk] goes to every rank
+__device__ __forceinline__ void t5_push_block(const HmyDev& st, int blk, unsigned int G) {
+    const size_t nD = t5_nD(st);
+    const int e0 = (int)((long long)blockIdx.x * (long long)nD / G), e1 = (int)((long long)(blockIdx.x + 1) * (long long)nD / G), len = e1 - e0;
+    const size_t slot = (((size_t)(st.x5_seq & 1u) * st.nblk + blk) * HMY_MAX_WORLD + st.xrank) * nD;
+    for (int idx = threadIdx.x; idx < len * st.xworld; idx += T5_EPI_THREADS) {
+        const int r = idx / len, e = e0 + (idx - r * len);
+        const float v = __ldcg(&st.Dnew[(size_t)blk * nD + e]);
+        st_volatile_v2(reinterpret_cast<uint2*>(st.xpeer[r] + st.x5_off_d) + slot + e, __float_as_uint(v), st.x5_seq);
     }
 }
 
@@ -430,7 +546,7 @@ struct T5Run { float o[HMY_MAX_V]; float rs; int upto; };
 
 // penalty rows {pen, sigma ln pen} of the slots in `need` (harmony.py:495-499); all 512 threads, quarter q = slot q,
 // thread-in-quarter = cluster
-template <int NC>
+template <int NC, bool MULTI>
 __device__ void t5_penalty_rows(const HmyDev& st, int mode, unsigned char* smem, const T5Lev& lev, T5Run& run,
                                 unsigned int need, unsigned int live, int blk) {
     constexpr int KT2 = 16 * NC;
@@ -440,8 +556,7 @@ __device__ void t5_penalty_rows(const HmyDev& st, int mode, unsigned char* smem,
         if (k < st.K) {
             if (mode == 1) out = make_float2(1.f, 0.f);
             else {
-                const size_t nBK = (size_t)st.B * st.K, nT = (size_t)st.nblk * nBK;
-                const float* ToldR = st.Told + nT; const float* DnewR = st.Dnew + nT;
+                const size_t nBK = (size_t)st.B * st.K, nD = nBK + st.K;
                 if (!((live >> j) & 1u)) {
                     // a slot this CTA has not met in this round: start from the previous stage's O
 #pragma unroll
@@ -450,18 +565,55 @@ __device__ void t5_penalty_rows(const HmyDev& st, int mode, unsigned char* smem,
                     run.upto = -1;
                 }
                 while (run.upto < blk) {
-                    const int i = ++run.upto;
-                    float a[HMY_MAX_V], r[HMY_MAX_V];
+                    const int i0 = run.upto + 1;
+                    if (i0 == blk) {
+                        // the usual single step: block blk-1's re-added sums in, block blk's removed sums out
+                        float a[HMY_MAX_V], r[HMY_MAX_V];
 #pragma unroll
-                    for (int v = 0; v < HMY_MAX_V; ++v) {
-                        const size_t e = (size_t)lev.get(v) * st.K + k;
-                        a[v] = (v < st.V && i > 0) ? __ldcg(&st.Dnew[(size_t)(i - 1) * nBK + e]) : 0.f;
-                        r[v] = (v < st.V) ? __ldcg(&st.Told[(size_t)i * nBK + e]) : 0.f;
+                        for (int v = 0; v < HMY_MAX_V; ++v) {
+                            const size_t e = (size_t)lev.get(v) * st.K + k;
+                            a[v] = (v < st.V && i0 > 0) ? t5_dnew<MULTI>(st, i0 - 1, e) : 0.f;
+                            r[v] = (v < st.V) ? st.Told[(size_t)i0 * nD + e] : 0.f;      // read-only in this launch: may sit in L1 (prefetched below)
+                        }
+                        const float ar = (i0 > 0) ? t5_dnew<MULTI>(st, i0 - 1, nBK + k) : 0.f, rr = st.Told[(size_t)i0 * nD + nBK + k];
+#pragma unroll
+                        for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] += a[v] - r[v];
+                        run.rs += ar - rr;
+                        run.upto = blk;
+                    } else {
+                        // a slot met for the first time in the middle of a round catches up on the finished blocks, four
+                        // steps per batch with all loads of a batch in flight (one round trip per batch, not per block:
+                        // the whole grid waits for the slowest CTA at the next barrier)
+                        const int i1 = min(blk - 1, i0 + 3);
+                        float acc[HMY_MAX_V];
+#pragma unroll
+                        for (int v = 0; v < HMY_MAX_V; ++v) acc[v] = 0.f;
+                        float accr = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = i0 + u;
+                            if (i <= i1) {
+#pragma unroll
+                                for (int v = 0; v < HMY_MAX_V; ++v)
+                                    if (v < st.V) {
+                                        const size_t e = (size_t)lev.get(v) * st.K + k;
+                                        acc[v] += ((i > 0) ? t5_dnew<MULTI>(st, i - 1, e) : 0.f) - __ldcg(&st.Told[(size_t)i * nD + e]);
+                                    }
+                                accr += ((i > 0) ? t5_dnew<MULTI>(st, i - 1, nBK + k) : 0.f) - __ldcg(&st.Told[(size_t)i * nD + nBK + k]);
+                            }
+                        }
+#pragma unroll
+                        for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] += acc[v];
+                        run.rs += accr;
+                        run.upto = i1;
                     }
-                    const float ar = (i > 0) ? __ldcg(&DnewR[(size_t)(i - 1) * st.K + k]) : 0.f, rr = __ldcg(&ToldR[(size_t)i * st.K + k]);
+                }
+                if (blk + 1 < st.nblk) {
+                    // the next block's removed sums are known already: pull them into L1 under this block's tiles
 #pragma unroll
-                    for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] += a[v] - r[v];
-                    run.rs += ar - rr;
+                    for (int v = 0; v < HMY_MAX_V; ++v)
+                        if (v < st.V) asm volatile("prefetch.global.L1 [%0];" ::"l"(&st.Told[(size_t)(blk + 1) * nD + (size_t)lev.get(v) * st.K + k]));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(&st.Told[(size_t)(blk + 1) * nD + nBK + k]));
                 }
                 float pen = 0.f;
 #pragma unroll
@@ -482,18 +634,20 @@ __device__ void t5_penalty_rows(const HmyDev& st, int mode, unsigned char* smem,
     t5_bar_sync(1, T5_EPI_THREADS);
 }
 
-// per-slot column sums of the finished tiles of this block -> the block's re-added sums (harmony.py:506-507)
-__device__ __forceinline__ void t5_flush_o(const HmyDev& st, unsigned int tmem, const T5Lev& lev, unsigned int mask, int blk) {
+// per-slot column sums of R since the previous flush -> the block's re-added sums (harmony.py:506-507).  The
+// accumulator runs over the whole round (it shares its MMAs with the per-next-block sums): `prev` is what it held at
+// the previous flush.
+__device__ __forceinline__ void t5_flush_o(const HmyDev& st, unsigned int tmem, const T5Lev& lev, unsigned int mask, int blk, float& prev) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp >> 2, k = 32 * (warp & 3) + lane;
     if ((mask >> q) & 1u) {                                  // warps of quarter q take slot q (lane = cluster)
-        const float v = t5_ld1(tmem + ((unsigned int)(32 * (warp & 3)) << 16) + T5_COL_O + 16u * q);
+        const float v = t5_ld1(tmem + ((unsigned int)(32 * (warp & 3)) << 16) + T5_COL_OT + 48u * q);
         t5_ld_wait();
-        const float x = v * (1.0f / HMY_OPSCALE);
+        const float x = (v - prev) * (1.0f / HMY_OPSCALE);
+        prev = v;
         if (k < st.K && x != 0.f) {
-            const size_t nBK = (size_t)st.B * st.K;
-            float* dn = st.Dnew + (size_t)blk * nBK;
+            float* dn = st.Dnew + (size_t)blk * t5_nD(st);
             for (int vv = 0; vv < st.V; ++vv) atomicAdd(&dn[(size_t)lev.get(vv) * st.K + k], x);
-            atomicAdd(&st.Dnew[(size_t)st.nblk * nBK + (size_t)blk * st.K + k], x);          // row sums (every cell has one level of covariate 0)
+            atomicAdd(&dn[(size_t)st.B * st.K + k], x);          // row sums
         }
     }
 }
@@ -502,7 +656,7 @@ __device__ __forceinline__ void t5_flush_t(const HmyDev& st, unsigned int tmem, 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp >> 2, k = 32 * (warp & 3) + lane;
     if ((mask >> q) & 1u) {
         float v[32];
-        const unsigned int ta = tmem + ((unsigned int)(32 * (warp & 3)) << 16) + T5_COL_T + 32u * q;
+        const unsigned int ta = tmem + ((unsigned int)(32 * (warp & 3)) << 16) + T5_COL_OT + 48u * q + 16u;
         t5_ld16(ta, v); t5_ld16(ta + 16u, v + 16);
         t5_ld_wait();
         if (k < st.K) {
@@ -510,8 +664,9 @@ __device__ __forceinline__ void t5_flush_t(const HmyDev& st, unsigned int tmem, 
             for (int nb = 0; nb < 32; ++nb) {
                 const float x = v[nb] * (1.0f / HMY_OPSCALE);
                 if (nb < st.nblk && x != 0.f) {
-                    for (int vv = 0; vv < st.V; ++vv) atomicAdd(&st.Told_next[((size_t)nb * st.B + lev.get(vv)) * st.K + k], x);
-                    atomicAdd(&st.Told_next[(size_t)st.nblk * st.B * st.K + (size_t)nb * st.K + k], x);
+                    float* tn = st.Told_next + (size_t)nb * t5_nD(st);
+                    for (int vv = 0; vv < st.V; ++vv) atomicAdd(&tn[(size_t)lev.get(vv) * st.K + k], x);
+                    atomicAdd(&tn[(size_t)st.B * st.K + k], x);
                 }
             }
         }
@@ -535,7 +690,12 @@ __device__ __forceinline__ void t5_grid_barrier(const HmyDev& st, unsigned long 
     t5_bar_sync(1, T5_EPI_THREADS);
 }
 
-template <int NC>
+// Timeline stamps (option "trace", thread 0): slot 0 start, 1 prologue done, per block b: 2 + 5 b + {0 first tile
+// staged, 1 penalty rows ready, 2 last tile handed to the accumulation, 3 block sums flushed, 4 grid barrier passed};
+// per tile i of block 5: 102 + 6 i + {0 scores ready, 1 scores in registers, 2 pass 1 done, 3 row sums met,
+// 4 operand tile free, 5 operand tile written}
+#define T5_STAMP(slot_) hmy_trace(st, (slot_))
+template <int NC, bool MULTI>
 __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, unsigned int bar0, unsigned int tmem,
                             unsigned int G, unsigned long long bar_base) {
     constexpr int KT2 = 16 * NC;
@@ -556,6 +716,9 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
     for (int v = 0; v < HMY_MAX_V; ++v) run.o[v] = 0.f;
     unsigned int live = 0u;                       // slots whose running rows are being followed
     bool had_cells = false;                       // D2y holds sums (tensor memory is not cleared by the allocation)
+    float o_prev = 0.f;                           // slot q's running column sum (this thread's cluster) at the last flush
+    bool first_of_block = true; int tile_in_block = 0;
+    T5_STAMP(1);
     for (;;) {
         const unsigned int s = t % T5_NZ, d = t & 1u;
         t5_wait(bar0 + 8u * (T5_B_ZFULL + s), (t / T5_NZ) & 1u);
@@ -565,20 +728,23 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         const int blk = hdr[T5_H_BLK];
         const bool empty = (flags & T5_F_EMPTY) != 0u;
         bool waited_acc = false;
+        if (first_of_block) { T5_STAMP(2 + 5 * blk); }
+        const int tslot = (blk == 5 && tile_in_block < 4) ? 102 + 6 * tile_in_block : HMY_TRACE_SLOTS;
         if (flags & T5_F_EVICT) {
             // the slot table starts over with this tile: everything accumulated under the old table leaves now
             if (t > 0) { t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u); t5_fence_after(); }
             waited_acc = true;
-            t5_flush_o(st, tmem, lev, bmask, blk);
+            t5_flush_o(st, tmem, lev, bmask, blk, o_prev);
             t5_flush_t(st, tmem, lev, rmask);
             t5_fence_before();
-            bmask = 0u; rmask = 0u; computed = 0u; live = 0u;
+            bmask = 0u; rmask = 0u; computed = 0u; live = 0u; o_prev = 0.f;
         }
         lev.w = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr + T5_H_LEV) + 16 * q);
         if (tmask & ~computed) {
-            t5_penalty_rows<NC>(st, mode, smem, lev, run, tmask & ~computed, live, blk);
+            t5_penalty_rows<NC, MULTI>(st, mode, smem, lev, run, tmask & ~computed, live, blk);
             computed |= tmask; live |= tmask;
         }
+        if (first_of_block) { T5_STAMP(3 + 5 * blk); first_of_block = false; }
         const unsigned int slotnb = reinterpret_cast<const unsigned short*>(meta + T5_META_SLOTNB)[row];
         const bool valid = slotnb != 0xFFFFu;
         const int slot = valid ? (int)(slotnb >> 8) : 0, nb = (int)(slotnb & 255u);
@@ -587,6 +753,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         // ---- scores of this thread's clusters (an empty tile still hands the accumulator back)
         t5_wait(bar0 + 8u * (T5_B_SFULL + d), (t >> 1) & 1u);
         t5_fence_after();
+        T5_STAMP(tslot);
         if (!empty) {
             const unsigned int ta = tmem + lane_base + T5_COL_D1 + 128u * d + (unsigned int)col0;
             t5_ld16(ta, E);
@@ -597,40 +764,79 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         t5_fence_before();
         __syncwarp();
         if (lane == 0) t5_arrive(bar0 + 8u * (T5_B_SFREE + d));
+        T5_STAMP(tslot + 1);
         if (!empty) {
             // ---- S = exp(-dist / sigma) (harmony.py:466-467) times the penalty (harmony.py:500)
             float ss = 0.f, sp = 0.f, sd = 0.f, se = 0.f, sg = 0.f;
             const float2* pr = pS + slot * KT2 + col0;
+            if (col0 + 8 * ng > st.K) {
+                // padding clusters (this quarter's tail): a score of -1e30 makes dist huge and S exactly 0
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                if (g < ng) {
+                for (int j = 0; j < 32; ++j) if (j < 8 * ng && col0 + j >= st.K) E[j] = -1.0e30f;
+            }
+            if (st.dbg & 4) { ss = 1.f; sp = 1.f; }
+            else if (st.sigma_uniform) {
+                const float c1u = -1.4426950408889634f / st.sigma_u;
 #pragma unroll
-                    for (int e2 = 0; e2 < 4; ++e2) {
-                        const float4 ck = *reinterpret_cast<const float4*>(cK + col0 + 8 * g + 2 * e2);
-                        const float4 pp = *reinterpret_cast<const float4*>(pr + 8 * g + 2 * e2);
-                        {
-                            const float dist = fmaf(E[8 * g + 2 * e2], -1.9073486328125e-6f, 2.0f);      // 2 (1 - z.y); scores carry 2^20
-                            const float sv = ex2_approx(dist * ck.x);
-                            const float ev = sv * pp.x;
-                            ss += sv; sp += ev;
-                            sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.y, se); sg = fmaf(ev, ck.y, sg);
-                            E[8 * g + 2 * e2] = ev;
+                for (int g = 0; g < 4; ++g) {
+                    if (g < ng) {
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const float4 pp = *reinterpret_cast<const float4*>(pr + 8 * g + 2 * e2);
+                            {
+                                const float dist = fmaf(E[8 * g + 2 * e2], -1.9073486328125e-6f, 2.0f);      // 2 (1 - z.y); scores carry 2^20
+                                const float sv = ex2_approx(dist * c1u);
+                                const float ev = sv * pp.x;
+                                ss += sv; sp += ev;
+                                sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.y, se);
+                                E[8 * g + 2 * e2] = ev;
+                            }
+                            {
+                                const float dist = fmaf(E[8 * g + 2 * e2 + 1], -1.9073486328125e-6f, 2.0f);
+                                const float sv = ex2_approx(dist * c1u);
+                                const float ev = sv * pp.z;
+                                ss += sv; sp += ev;
+                                sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.w, se);
+                                E[8 * g + 2 * e2 + 1] = ev;
+                            }
                         }
-                        {
-                            const float dist = fmaf(E[8 * g + 2 * e2 + 1], -1.9073486328125e-6f, 2.0f);
-                            const float sv = ex2_approx(dist * ck.z);
-                            const float ev = sv * pp.z;
-                            ss += sv; sp += ev;
-                            sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.w, se); sg = fmaf(ev, ck.w, sg);
-                            E[8 * g + 2 * e2 + 1] = ev;
+                    }
+                }
+                sg = st.sigma_u * sp;                   // sum_k sigma_k ev_k
+            } else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g < ng) {
+#pragma unroll
+                        for (int e2 = 0; e2 < 4; ++e2) {
+                            const float4 ck = *reinterpret_cast<const float4*>(cK + col0 + 8 * g + 2 * e2);
+                            const float4 pp = *reinterpret_cast<const float4*>(pr + 8 * g + 2 * e2);
+                            {
+                                const float dist = fmaf(E[8 * g + 2 * e2], -1.9073486328125e-6f, 2.0f);
+                                const float sv = ex2_approx(dist * ck.x);
+                                const float ev = sv * pp.x;
+                                ss += sv; sp += ev;
+                                sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.y, se); sg = fmaf(ev, ck.y, sg);
+                                E[8 * g + 2 * e2] = ev;
+                            }
+                            {
+                                const float dist = fmaf(E[8 * g + 2 * e2 + 1], -1.9073486328125e-6f, 2.0f);
+                                const float sv = ex2_approx(dist * ck.z);
+                                const float ev = sv * pp.z;
+                                ss += sv; sp += ev;
+                                sd = fmaf(ev, dist, sd); se = fmaf(ev, pp.w, se); sg = fmaf(ev, ck.w, sg);
+                                E[8 * g + 2 * e2 + 1] = ev;
+                            }
                         }
                     }
                 }
             }
             // ---- the four threads of a cell meet: sums over all clusters
             float2* xs = xch + (t & 1u) * 512;
+            T5_STAMP(tslot + 2);
             xs[q * 128 + row] = make_float2(ss, sp);
             t5_bar_sync(2 + rq, 128);
+            T5_STAMP(tslot + 3);
             float sst = 0.f, spt = 0.f;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) { const float2 u = xs[qq * 128 + row]; sst += u.x; spt += u.y; }
@@ -644,6 +850,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
             }
             // ---- operand tiles of the accumulation: wait until the previous tile's MMAs have read them
             if (t > 0 && !waited_acc) t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u);
+            T5_STAMP(tslot + 4);
             const float sc1024 = sc * HMY_OPSCALE;
             unsigned char* Rh = smem + T5_OFF_RH + (row >> 3) * T5_R_LBO + (row & 7) * 16;
             float* Rg = st.R + (size_t)cell * st.Kp;
@@ -656,8 +863,10 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
                     split2(E[8 * g + 2] * sc1024, E[8 * g + 3] * sc1024, hi.y, lo.y);
                     split2(E[8 * g + 4] * sc1024, E[8 * g + 5] * sc1024, hi.z, lo.z);
                     split2(E[8 * g + 6] * sc1024, E[8 * g + 7] * sc1024, hi.w, lo.w);
-                    *reinterpret_cast<uint4*>(Rh + (g0 + g) * T5_R_SBO) = hi;
-                    *reinterpret_cast<uint4*>(Rh + T5_SZ_RPART + (g0 + g) * T5_R_SBO) = lo;
+                    if (!(st.dbg & 8)) {
+                        *reinterpret_cast<uint4*>(Rh + (g0 + g) * T5_R_SBO) = hi;
+                        *reinterpret_cast<uint4*>(Rh + T5_SZ_RPART + (g0 + g) * T5_R_SBO) = lo;
+                    }
                     if (wr) {
                         const int c = col0 + 8 * g;
                         if (c < st.Kp) *reinterpret_cast<float4*>(Rg + c) = make_float4(E[8 * g] * sc, E[8 * g + 1] * sc, E[8 * g + 2] * sc, E[8 * g + 3] * sc);
@@ -673,7 +882,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
                     const int p = (nb & 7) >> 1;
                     w.x = p == 0 ? h : 0u; w.y = p == 1 ? h : 0u; w.z = p == 2 ? h : 0u; w.w = p == 3 ? h : 0u;
                 }
-                *reinterpret_cast<uint4*>(smem + T5_OFF_NB + q * T5_R_SBO + (row >> 3) * T5_R_LBO + (row & 7) * 16) = w;
+                *reinterpret_cast<uint4*>(smem + T5_OFF_NB + (2 + q) * T5_R_SBO + (row >> 3) * T5_R_LBO + (row & 7) * 16) = w;
             }
             bmask |= tmask; rmask |= tmask; had_cells = true;
         } else {
@@ -682,18 +891,24 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         t5_fence_async();
         __syncwarp();
         if (lane == 0) t5_arrive(bar0 + 8u * T5_B_RFULL);
-        ++t;
+        T5_STAMP(tslot + 5);
+        ++t; ++tile_in_block;
         if (flags & T5_F_LAST_BLOCK) {
+            T5_STAMP(4 + 5 * blk);
+            first_of_block = true; tile_in_block = 0;
             // ---- end of the block: its sums join the running O, the next block's removed sums leave it
             t5_wait(bar0 + 8u * T5_B_ODONE, nblocks_done & 1u);
             t5_fence_after();
             ++nblocks_done;
-            t5_flush_o(st, tmem, lev, bmask, blk);
+            t5_flush_o(st, tmem, lev, bmask, blk, o_prev);
             bmask = 0u; computed = 0u;
+            T5_STAMP(5 + 5 * blk);
             const bool last = (flags & T5_F_LAST_ROUND) != 0u;
             if (!last) {
                 t5_fence_before();
                 t5_grid_barrier(st, bar_next += G);
+                if (MULTI) t5_push_block(st, blk, G);          // this rank's part of the block's sums goes to every rank
+                T5_STAMP(6 + 5 * blk);
             } else {
                 // ---- end of the round: centroid sums, next round's removed sums, objective sums
                 t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u);
@@ -716,6 +931,43 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
                 if (lane == 0) { atomicAdd(&st.obj[0], a); atomicAdd(&st.obj[1], b); }
                 t5_fence_before();
                 t5_grid_barrier(st, bar_next += G);
+                T5_STAMP(6 + 5 * blk);
+                if (MULTI) {
+                    // ---- this rank's sums are complete: its slices of every small table go to every rank
+                    t5_push_block(st, blk, G);
+                    const unsigned int seq = st.x5_seq, par = seq & 1u;
+                    const int W = st.xworld, me = st.xrank;
+                    const size_t nD = t5_nD(st), nT = (size_t)st.nblk * nD, nY = (size_t)st.K * st.dp + 2;
+                    {
+                        const long long e0 = (long long)blockIdx.x * (long long)nT / G, e1 = (long long)(blockIdx.x + 1) * (long long)nT / G, len = e1 - e0;
+                        for (long long idx = tid; idx < len * W; idx += T5_EPI_THREADS) {
+                            const int r = (int)(idx / len); const size_t e = (size_t)(e0 + (idx - (long long)r * len));
+                            st_volatile_v2(reinterpret_cast<uint2*>(st.xpeer[r] + st.x5_off_t) + ((size_t)par * HMY_MAX_WORLD + me) * nT + e,
+                                           __float_as_uint(__ldcg(&st.Told_next[e])), seq);
+                        }
+                    }
+                    {
+                        const long long e0 = (long long)blockIdx.x * (long long)nY / G, e1 = (long long)(blockIdx.x + 1) * (long long)nY / G, len = e1 - e0;
+                        for (long long idx = tid; idx < len * W; idx += T5_EPI_THREADS) {
+                            const int r = (int)(idx / len); const size_t e = (size_t)(e0 + (idx - (long long)r * len));
+                            const double v = (e < nY - 2) ? __ldcg(&st.Yacc[e]) : __ldcg(&st.obj[e - (nY - 2)]);
+                            const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+                            uint2* dst = reinterpret_cast<uint2*>(st.xpeer[r] + st.x5_off_y) + ((size_t)par * HMY_MAX_WORLD + me) * 2 * nY + 2 * e;
+                            st_volatile_v2(dst, (unsigned int)bits, seq);
+                            st_volatile_v2(dst + 1, (unsigned int)(bits >> 32), seq);
+                        }
+                    }
+                    {
+                        // the next round's removed sums, summed over ranks (this CTA's slice; rank order: identical everywhere)
+                        const long long e0 = (long long)blockIdx.x * (long long)nT / G, e1 = (long long)(blockIdx.x + 1) * (long long)nT / G;
+                        const uint2* src = reinterpret_cast<const uint2*>(st.xpeer[me] + st.x5_off_t) + (size_t)par * HMY_MAX_WORLD * nT;
+                        for (long long e = e0 + tid; e < e1; e += T5_EPI_THREADS) {
+                            float sum = 0.f;
+                            for (int r = 0; r < W; ++r) sum += t5_ll_read(src + (size_t)r * nT + (size_t)e, seq);
+                            st.Told_next[e] = sum;
+                        }
+                    }
+                }
                 break;
             }
         }
@@ -726,30 +978,65 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         // cross-entropy term of the objective (harmony.py:404-411 collapsed to K x B)
         const int nblocks = (mode == 1) ? 1 : st.nblk;
         const size_t nBK = (size_t)st.B * st.K;
-        const float* DnewR = st.Dnew + (size_t)st.nblk * nBK;
         const int n = (int)nBK;
         const int e0 = (int)((long long)blockIdx.x * n / G), e1 = (int)((long long)(blockIdx.x + 1) * n / G);
         double part = 0.0;
         for (int e = e0 + tid; e < e1; e += T5_EPI_THREADS) {
             const int b = e / st.K, k = e - b * st.K;
             double o = 0.0, rs = 0.0;
-            for (int i = 0; i < nblocks; ++i) { o += (double)__ldcg(&st.Dnew[(size_t)i * nBK + e]); rs += (double)__ldcg(&DnewR[(size_t)i * st.K + k]); }
+            for (int i = 0; i < nblocks; ++i) { o += (double)t5_dnew<MULTI>(st, i, (size_t)e); rs += (double)t5_dnew<MULTI>(st, i, nBK + k); }
             st.O[e] = o;
             const float oc = fmaxf((float)o, 1e-8f), ec = fmaxf((float)(rs * (double)st.Pr_b[b]), 1e-8f);
             part += (double)st.sigma[k] * (double)st.theta[b] * (double)logf((oc + ec) / ec) * o;
         }
-        part = warp_sum_d(part);
-        if (lane == 0 && part != 0.0) atomicAdd(&st.obj[2], part);
+        if (!MULTI) {
+            part = warp_sum_d(part);
+            if (lane == 0 && part != 0.0) atomicAdd(&st.obj[2], part);
+        } else if (part != 0.0) {
+            // every rank computes this term from the same tables; summed in 2^-30 fixed point so that the order of
+            // the atomics cannot make the ranks' objectives (and with them their convergence decisions) differ
+            atomicAdd(reinterpret_cast<unsigned long long*>(&st.obj[3]), (unsigned long long)__double2ll_rn(part * 1073741824.0));
+        }
         // row sums the next round starts from, unit centroids of the next round (harmony.py:443-444)
         for (int k = blockIdx.x * T5_EPI_WARPS + warp; k < st.K; k += G * T5_EPI_WARPS) {
-            double rs = (lane < nblocks) ? (double)__ldcg(&DnewR[(size_t)lane * st.K + k]) : 0.0;
+            double rs = (lane < nblocks) ? (double)t5_dnew<MULTI>(st, lane, nBK + k) : 0.0;
             rs = warp_sum_d(rs);
             if (lane == 0) st.Rsum_next[k] = rs;
-            double y0 = (lane < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + lane]) : 0.0;
-            double y1 = (lane + 32 < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + lane + 32]) : 0.0;
+            double y0 = 0.0, y1 = 0.0;
+            if (!MULTI) {
+                y0 = (lane < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + lane]) : 0.0;
+                y1 = (lane + 32 < st.d) ? __ldcg(&st.Yacc[(size_t)k * st.dp + lane + 32]) : 0.0;
+            } else {
+                const size_t nY = (size_t)st.K * st.dp + 2;
+                const uint2* src = reinterpret_cast<const uint2*>(st.xpeer[st.xrank] + st.x5_off_y) + (size_t)(st.x5_seq & 1u) * HMY_MAX_WORLD * 2 * nY;
+                for (int r = 0; r < st.xworld; ++r) {
+                    if (lane < st.d) {
+                        const uint2* pz = src + (size_t)r * 2 * nY + 2 * ((size_t)k * st.dp + lane);
+                        const unsigned long long lo = __float_as_uint(t5_ll_read(pz, st.x5_seq)), hi = __float_as_uint(t5_ll_read(pz + 1, st.x5_seq));
+                        y0 += __longlong_as_double((long long)((hi << 32) | lo));
+                    }
+                    if (lane + 32 < st.d) {
+                        const uint2* pz = src + (size_t)r * 2 * nY + 2 * ((size_t)k * st.dp + lane + 32);
+                        const unsigned long long lo = __float_as_uint(t5_ll_read(pz, st.x5_seq)), hi = __float_as_uint(t5_ll_read(pz + 1, st.x5_seq));
+                        y1 += __longlong_as_double((long long)((hi << 32) | lo));
+                    }
+                }
+            }
             const double inv = 1.0 / sqrt(warp_sum_d(y0 * y0 + y1 * y1));
             if (lane < st.dp) st.Ynext[(size_t)k * st.dp + lane] = (lane < st.d) ? (float)(y0 * inv) : 0.f;
             if (lane + 32 < st.dp) st.Ynext[(size_t)k * st.dp + lane + 32] = (lane + 32 < st.d) ? (float)(y1 * inv) : 0.f;
+        }
+        if (MULTI && blockIdx.x == 0 && tid < 2) {
+            // objective sums over all ranks (rank order) for the host
+            const size_t nY = (size_t)st.K * st.dp + 2;
+            const uint2* src = reinterpret_cast<const uint2*>(st.xpeer[st.xrank] + st.x5_off_y) + (size_t)(st.x5_seq & 1u) * HMY_MAX_WORLD * 2 * nY;
+            double sum = 0.0;
+            for (int r = 0; r < st.xworld; ++r) {
+                const uint2* pz = src + (size_t)r * 2 * nY + 2 * (nY - 2 + tid);
+                const unsigned long long lo = __float_as_uint(t5_ll_read(pz, st.x5_seq)), hi = __float_as_uint(t5_ll_read(pz + 1, st.x5_seq));
+                sum += __longlong_as_double((long long)((hi << 32) | lo));
+            }
+            st.obj_out[tid] = sum;
         }
     }
 }
@@ -757,12 +1044,15 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
 // ---- kernel -----------------------------------------------------------------------------------------------------------
 // mode 0: one k-means round; mode 1: the assignment of init_cluster (harmony.py:377-392: no penalty, all cells,
 // storage order).  bar_base: value of the grid-barrier counter when the launch starts.
-template <int NC>
+template <int NC, bool MULTI>
 __global__ void __launch_bounds__(T5_THREADS, 1) k_round_tc5(HmyDev st, int mode, unsigned long long bar_base) {
     extern __shared__ __align__(1024) unsigned char smem_t5[];
     unsigned char* const smem = smem_t5;
     constexpr int KT2 = 16 * NC;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // warp index through a shuffle: the compiler then knows the role dispatch below is warp-uniform (without that the
+    // MMA warp's code counts as divergent and every descriptor is moved into uniform registers again for every MMA)
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const unsigned int G = gridDim.x;
     const unsigned int bar0 = smem_u32(smem + t5_off_bar(NC));
     unsigned int* s_tmem = reinterpret_cast<unsigned int*>(smem + t5_off_bar(NC) + 128);
@@ -804,9 +1094,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_round_tc5(HmyDev st, int mode
     }
     {
         uint4* z = reinterpret_cast<uint4*>(smem);
-        for (int i = tid; i < T5_OFF_ONES / 16; i += T5_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);        // Z stages | R tiles | one-hot tile
-        unsigned int* ones = reinterpret_cast<unsigned int*>(smem + T5_OFF_ONES);
-        for (int i = tid; i < 128; i += T5_THREADS) ones[i] = 0x3C003C00u;
+        for (int i = tid; i < T5_OFF_YH / 16; i += T5_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);          // Z stages | R tiles | one-hot tile
+        __syncthreads();
+        unsigned int* ones = reinterpret_cast<unsigned int*>(smem + T5_OFF_NB);
+        for (int i = tid; i < 2 * 2048 / 4; i += T5_THREADS) ones[i] = 0x3C003C00u;                         // 16 columns of 1.0
         float2* ps = reinterpret_cast<float2*>(smem + t5_off_ps(NC));
         for (int i = tid; i < T5_SLOTS * KT2; i += T5_THREADS) ps[i] = make_float2(0.f, 0.f);
     }
@@ -815,9 +1106,10 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_round_tc5(HmyDev st, int mode
     __syncthreads();
     t5_fence_after();
     const unsigned int tmem = *s_tmem;
+    hmy_trace(st, 0);
     if (warp == T5_WARP_PROD) t5_producer<NC>(st, mode, smem, bar0, G);
-    else if (warp == T5_WARP_MMA) { if (lane == 0) t5_mma_thread<NC>(st, smem, bar0, tmem); __syncwarp(); }
-    else t5_epilogue<NC>(st, mode, smem, bar0, tmem, G, bar_base);
+    else if (warp == T5_WARP_MMA) t5_mma_warp<NC>(st, smem, bar0, tmem);
+    else t5_epilogue<NC, MULTI>(st, mode, smem, bar0, tmem, G, bar_base);
     t5_fence_before();
     __syncthreads();
     if (warp == T5_WARP_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512));

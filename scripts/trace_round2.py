@@ -30,7 +30,7 @@ def worker(rank, world, port):
     torch.cuda.synchronize(); dist.barrier()
     ho.kmeans_round()
     G = eng.counter("grid"); nblk = eng.counter("nblk")
-    buf = np.zeros((G + 1, 128), dtype=np.uint64)
+    buf = np.zeros((G + 1, 192), dtype=np.uint64)
     eng._ck(eng.lib.hmy_get(eng.h, 9, buf.ctypes.data_as(C.c_void_p), buf.nbytes), "trace")
     if rank == 0:
         t = buf[:G].astype(np.int64); ser = buf[G].astype(np.int64).reshape(32, 4)

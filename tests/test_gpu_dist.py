@@ -1,5 +1,6 @@
-"""Cells sharded over 2 GPUs (one process per GPU, NCCL): the staged multi-GPU mode must give
-the single-GPU / reference result.  Needs >= 2 CUDA devices (skipped otherwise)."""
+"""Cells sharded over 2 / 4 / 8 GPUs (one process per GPU): the fused mode (in-kernel peer exchange; the tensor-memory
+round kernel where its shape limits hold) and the staged NCCL mode must give the single-GPU / reference result.
+Needs as many CUDA devices as ranks (skipped otherwise)."""
 import os
 import socket
 
@@ -34,35 +35,40 @@ def _worker(rank, world, port, q, name, fused, relaxed=0):
                      engine_options={"fused": fused, "relaxed": relaxed})
         Zc = ho.Z_corr                      # gathered over ranks
         q.put(dict(rank=rank, rounds=list(ho.kmeans_rounds), Z=Zc, obj=list(ho.objective_harmony),
-                   lo=ho._lo, hi=ho._hi, fused=ho._engine.counter("fused")))
+                   lo=ho._lo, hi=ho._hi, fused=ho._engine.counter("fused"), tc5=ho._engine.counter("tc5")))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("fused", [1, 0])
-@pytest.mark.parametrize("name", ["synth", "pbmc"])
-def test_two_gpus_match_reference(name, fused):
+@pytest.mark.parametrize("world,fused", [(2, 1), (2, 0), (4, 1), (8, 1)])
+@pytest.mark.parametrize("name", ["synth", "pbmc", "ircolitis"])
+def test_sharded_runs_match_reference(name, world, fused):
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    if name == "ircolitis" and not fused:
+        pytest.skip("the staged mode is covered by the two small cases")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, name, fused)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, name, fused)) for r in range(world)]
     for p in procs:
         p.start()
-    outs = sorted([q.get(timeout=600) for _ in procs], key=lambda o: o["rank"])
+    outs = sorted([q.get(timeout=900) for _ in procs], key=lambda o: o["rank"])
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
     inp, gold = load_case(name)
-    a, b = outs
-    assert a["fused"] == b["fused"] == fused
-    assert a["rounds"] == b["rounds"] == list(gold["kmeans_rounds"])
-    np.testing.assert_array_equal(a["Z"], b["Z"])
+    a = outs[0]
+    for b in outs[1:]:
+        assert b["fused"] == a["fused"] == fused and b["tc5"] == a["tc5"]
+        assert b["rounds"] == a["rounds"]
+        np.testing.assert_array_equal(a["Z"], b["Z"])          # every rank holds the same gathered result
+    assert a["tc5"] == fused                                    # fused sharded runs are on the tensor-memory kernel
+    assert a["rounds"] == list(gold["kmeans_rounds"])
     err = rel_max(a["Z"][gold["final_cells"]], gold["Zcorr_final"])
-    print(f"\n[{name}] 2-GPU {"fused" if fused else "staged"} mode: final Z_corr vs reference fp32 {err:.3e}")
+    print(f"\n[{name}] {world} GPUs, {'fused' if fused else 'staged'} mode: final Z_corr vs reference fp32 {err:.3e}")
     assert err < 1e-4
     np.testing.assert_allclose(a["obj"], gold["objective_harmony"], rtol=5e-5)
 
