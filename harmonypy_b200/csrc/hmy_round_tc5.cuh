@@ -68,6 +68,7 @@ __host__ __device__ constexpr int t5_smem_bytes(int NC) { return t5_off_bar(NC) 
 #define T5_H_FLAGS 0
 #define T5_H_BLK 1
 #define T5_H_MASK 2              // slots used by this tile
+#define T5_H_ALLOC 3             // slots that have a combination
 #define T5_H_COMBO 4             // [4] combination of every slot (-1: free)
 #define T5_H_KSLOT 8             // [2] slot of every 16-row K step, one byte each (0xFF: no cells)
 #define T5_H_LEV 12              // u16 [4][8] one-hot rows of every slot's combination (16-byte aligned)
@@ -199,6 +200,20 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
     bool pending = false;                                      // tile t-1's copies are in flight, its zfull not yet signalled
     const int nblocks = (mode == 1) ? 1 : st.nblk;
     const unsigned int sbase = smem_u32(smem);
+    if (mode != 1) {
+        // The i-th share of every block's position-sorted list lies around the i-th share of the position range: the
+        // combinations there get their slots up front, so that the epilogue follows their running O rows from block 0
+        // (a slot first met in the middle of a round has to catch up on every finished block -- the whole grid waits)
+        const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G, m = (c1 - c0) / 2;
+        const long long probe[4] = {c0, max(c1 - 1, c0), max(c0 - m, 0LL), min(c1 - 1 + m, st.N - 1)};
+        for (int i = 0; i < 4 && st.N > 0; ++i) {
+            const int c = st.combo[probe[i]];
+            if (c == sc0 || c == sc1 || c == sc2 || c == sc3 || nslots == T5_SLOTS) continue;
+            const int slot = nslots++;
+            if (slot == 0) sc0 = c; else if (slot == 1) sc1 = c; else if (slot == 2) sc2 = c; else sc3 = c;
+            if ((lane >> 3) == slot) mylev = (unsigned short)(((lane & 7) < st.V) ? st.combo_lev[c * st.V + (lane & 7)] : 0);
+        }
+    }
     for (int blk = 0; blk < nblocks; ++blk) {
         long long lb, le;
         if (mode == 1) { lb = (long long)blockIdx.x * st.N / G; le = (long long)(blockIdx.x + 1) * st.N / G; }
@@ -297,7 +312,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
             reinterpret_cast<unsigned short*>(hdr + T5_H_LEV)[lane] = mylev;
             __syncwarp();
             if (lane == 0) {
-                hdr[T5_H_FLAGS] = (int)flags; hdr[T5_H_BLK] = blk; hdr[T5_H_MASK] = (int)mask;
+                hdr[T5_H_FLAGS] = (int)flags; hdr[T5_H_BLK] = blk; hdr[T5_H_MASK] = (int)mask; hdr[T5_H_ALLOC] = (1 << nslots) - 1;
                 hdr[T5_H_COMBO + 0] = sc0; hdr[T5_H_COMBO + 1] = sc1; hdr[T5_H_COMBO + 2] = sc2; hdr[T5_H_COMBO + 3] = sc3;
                 hdr[T5_H_KSLOT] = (int)ks_lo; hdr[T5_H_KSLOT + 1] = (int)ks_hi;
             }
@@ -480,7 +495,14 @@ __device__ void t5_mma_warp(const HmyDev& st, unsigned char* smem, unsigned int 
             if (f_lastr) break;
         }
         if (progressed) { idle = 0; idle_t0 = 0; }
-        else if ((++idle & 255u) == 0u) {                 // nothing to issue for seconds: an error, not a hang
+        else {
+            // nothing to issue: sleep on the barrier that normally completes next (try_wait suspends the warp until
+            // the phase completes or a time limit passes) instead of spinning -- a busy poll loop here took issue slots
+            // from the four epilogue warps of this scheduler, i.e. from a quarter of every tile's rows
+            if (ta < ts) (void)t5_test(bar0 + 8u * T5_B_RFULL, ta & 1u);
+            else if (!score_end) (void)t5_test(bar0 + 8u * (T5_B_ZFULL + ts % T5_NZ), (ts / T5_NZ) & 1u);
+        }
+        if (!progressed && (++idle & 255u) == 0u) {        // nothing to issue for seconds: an error, not a hang
             unsigned long long tn; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tn));
             if (idle_t0 == 0) idle_t0 = tn; else if (tn - idle_t0 > 4000000000ull) __trap();
         }
@@ -740,9 +762,14 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
             bmask = 0u; rmask = 0u; computed = 0u; live = 0u; o_prev = 0.f;
         }
         lev.w = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(hdr + T5_H_LEV) + 16 * q);
-        if (tmask & ~computed) {
-            t5_penalty_rows<NC, MULTI>(st, mode, smem, lev, run, tmask & ~computed, live, blk);
-            computed |= tmask; live |= tmask;
+        {
+            // the first tile of a block brings the rows of ALL slots with a combination up to date (slot q = quarter q:
+            // it costs no more time than one slot, and no slot ever falls behind); later tiles only add new slots
+            const unsigned int want = (first_of_block ? (unsigned int)hdr[T5_H_ALLOC] : tmask) & ~computed;
+            if (want) {
+                t5_penalty_rows<NC, MULTI>(st, mode, smem, lev, run, want, live, blk);
+                computed |= want; live |= want;
+            }
         }
         if (first_of_block) { T5_STAMP(3 + 5 * blk); first_of_block = false; }
         const unsigned int slotnb = reinterpret_cast<const unsigned short*>(meta + T5_META_SLOTNB)[row];
