@@ -318,20 +318,33 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
             }
             __syncwarp();
             hmy_trace_any(st, psl + 1);
-            // ---- gather: 8 rows x 4 chunks of 16 bytes per instruction (conflict-free core-matrix writes)
+            // ---- gather: 8 rows x 4 chunks of 16 bytes per instruction (conflict-free core-matrix writes).  Straight-line
+            // code: the cell ids of this lane's 16 rows first (one batch of shared-memory loads), then nothing but copies
             {
                 const int r8 = lane & 7, cs = lane >> 3;
-                const unsigned int zs = sbase + T5_OFF_Z + s * T5_SZ_STAGE;
+                const unsigned int zs = sbase + T5_OFF_Z + s * T5_SZ_STAGE + (unsigned int)r8 * 16u;
                 const int ngroups = (nrows + 7) >> 3;
-                for (int g = 0; g < ngroups; ++g) {
-                    const int row = 8 * g + r8;
-                    const bool valid = mslot[row] != 0xFFFFu;
-                    const unsigned char* src = Zs + (size_t)mcell[row] * zrow;
-                    const unsigned int drow = zs + (unsigned int)g * T5_SBO_K + (unsigned int)r8 * 16u;
-                    for (int cq = 0; cq < dt; ++cq) {
-                        const int ch = 4 * cq + cs;                    // chunk of the row: [0, 2 dt) hi, [2 dt, 4 dt) lo
-                        const int part = (ch >= 2 * dt) ? 1 : 0, cc = ch - part * 2 * dt;
-                        if (valid) t5_cp16(drow + (unsigned int)part * T5_SZ_ZPART + (unsigned int)cc * T5_LBO_K, src + ch * 16);
+                int cg[16]; unsigned int vmask = 0u;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    cg[g] = mcell[8 * g + r8];
+                    if (g < ngroups && mslot[8 * g + r8] != 0xFFFFu) vmask |= 1u << g;
+                }
+                unsigned int doff[4]; int soff[4];
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    const int ch = 4 * cq + cs;                    // chunk of the row: [0, 2 dt) hi, [2 dt, 4 dt) lo
+                    const int part = (ch >= 2 * dt) ? 1 : 0, cc = ch - part * 2 * dt;
+                    doff[cq] = (unsigned int)part * T5_SZ_ZPART + (unsigned int)cc * T5_LBO_K; soff[cq] = ch * 16;
+                }
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    if ((vmask >> g) & 1u) {
+                        const unsigned char* src = Zs + (size_t)cg[g] * zrow;
+                        const unsigned int drow = zs + (unsigned int)g * T5_SBO_K;
+#pragma unroll
+                        for (int cq = 0; cq < 4; ++cq)
+                            if (cq < dt) t5_cp16(drow + doff[cq], src + soff[cq]);
                     }
                 }
                 asm volatile("cp.async.commit_group;" ::: "memory");
