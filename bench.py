@@ -297,12 +297,15 @@ def run_reference(args, w):
     print(json.dumps(out), flush=True)
 
 
-def golden_parity(device_index):
+def golden_parity(device_index, comm=None):
     """Second half of the metric: Z_corr max|d|/max|Z| vs the REFERENCE's stored output on the
     bundled datasets (fixtures under tests/golden, generated from the real harmonypy), through the
-    public class with the reference permutation stream.  A few seconds; rank 0 only."""
+    public class with the reference permutation stream.  A few seconds.  With more than one rank the
+    datasets run SHARDED over all ranks of the job (every rank calls this; same engine mode as the
+    timed runs), so the line carries the parity of the N-GPU path, not of a single-GPU side run."""
     from harmonypy_b200.harmony import Harmony, Problem
-    out = {"tolerance": 1e-4, "norm": "max|Z - Z_ref| / max|Z_ref|"}
+    n_ranks = 1 if comm is None else comm.world
+    out = {"tolerance": 1e-4, "norm": "max|Z - Z_ref| / max|Z_ref|", "n_ranks": n_ranks}
     for name, label in (("pbmc", "pbmc_3500"), ("ircolitis", "ircolitis_blood_cd8")):
         try:
             inp = np.load(os.path.join(ROOT, "tests", "golden", f"{name}_input.npz"))
@@ -315,8 +318,8 @@ def golden_parity(device_index):
         t0 = time.perf_counter()
         ho = Harmony(prob, float(inp["alpha"]), int(inp["max_iter_harmony"]), int(inp["max_iter_kmeans"]),
                      float(inp["epsilon_kmeans"]), float(inp["epsilon_harmony"]), float(inp["block_size"]), False,
-                     int(inp["random_state"]), device_index, init_centroids=inp["Y0"])
-        Zc = ho.Z_corr
+                     int(inp["random_state"]), device_index, init_centroids=inp["Y0"], comm=comm)
+        Zc = ho.Z_corr                      # gathered over the ranks
         dt = time.perf_counter() - t0
         ref, ref64 = gold["Zcorr_final"], gold["Zcorr_final_f64"]
         cells = gold["final_cells"]
@@ -324,7 +327,9 @@ def golden_parity(device_index):
             "vs_reference_fp32": float(np.abs(Zc[cells] - ref).max() / np.abs(ref).max()),
             "vs_reference_fp64_arbiter": float(np.abs(Zc[cells] - ref64).max() / np.abs(ref64).max()),
             "kmeans_rounds_equal": list(map(int, ho.kmeans_rounds)) == list(map(int, gold["kmeans_rounds"])),
-            "cells": int(Zc.shape[0]), "seconds_incl_upload": dt,
+            "cells": int(Zc.shape[0]), "seconds_incl_upload": dt, "n_ranks": n_ranks,
+            "round_kernel": "k_round_tc5" if ho._engine.counter("tc5") == 1 else "k_round_mma",
+            "fused_exchange": ho._engine.counter("fused") == 1,
         }
         del ho
     return out
@@ -414,20 +419,25 @@ def run_ours(args, w):
     peak, peak_src = measured_peak_gbs()
     ach_round = (b_round * n_local * n_rounds) / (ms_round / 1e3) / 1e9 if ms_round > 0 else 0.0
     ach_ridge = (b_ridge * n_local * n_ridge) / (ms_ridge / 1e3) / 1e9 if ms_ridge > 0 else 0.0
-    traffic = None
+    tc5 = eng.counter("tc5") == 1
+    traffic, traffic_source = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("workload") == args.workload:
-            traffic = tj.get("k_round_dram_bytes_per_launch")
+        ent = tj.get("k_round_tc5" if tc5 else "k_round_mma")
+        if tj.get("workload") == args.workload and ent:
+            traffic = ent.get("dram_bytes_per_launch")
+            traffic_source = "static: %s; %s" % (ent.get("capture"), ent.get("note", ""))
     except Exception:
         pass
-    tc5 = eng.counter("tc5") == 1
-    if tc5:
-        traffic = None                      # profiles/traffic.json was captured for k_round_mma
-    roofline = {"bound": "hbm", "kernel": ("k_round_tc5 (tcgen05 / tensor-memory round kernel, opt-in)" if tc5 else
-                                           "k_round (one k-means round, persistent cooperative kernel)"),
+    roofline = {"bound": "hbm", "kernel": ("k_round_tc5<NC> (tcgen05 / tensor-memory round kernel: producer warp + MMA warp + 16 epilogue warps)" if tc5 else
+                                           "k_round_mma (one k-means round, persistent cooperative kernel, mma.sync)"),
                 "achieved": ach_round, "peak": peak, "unit": "GB/s", "frac": ach_round / peak, "traffic": traffic,
+                "traffic_source": traffic_source,
+                "note": ("achieved = SURVEY 8(d) algorithmic bytes (4d + 8K + 4V + 4 per cell and round) / measured launch time; "
+                         "the kernel itself moves fewer bytes than that definition: it never re-reads R (phase 0 folded into the "
+                         "previous round's accumulation) and stores R only in the rounds after which cluster() can stop"
+                         if tc5 else None),
                 "peak_source": peak_src, "algorithmic_bytes_per_cell": b_round,
                 "bytes_per_launch": b_round * n_local, "avg_launch_ms": ms_round / max(n_rounds, 1),
                 "launches_timed": n_rounds, "share_of_step": ms_round / ms_total,
@@ -468,8 +478,8 @@ def run_ours(args, w):
                "kind": r["kind"], "seconds": r["loop_seconds"], "sample": r["sample"]}
 
     parity = None
-    if rank == 0 and not args.no_parity:
-        parity = golden_parity(local_rank)
+    if not args.no_parity:
+        parity = golden_parity(local_rank, comm)          # all ranks: the datasets run sharded over the job's GPUs
     if rank == 0:
         out = {
             "metric": "cells/sec to convergence (full Harmony loop)", "value": value, "unit": "cells/s",
