@@ -13,6 +13,8 @@
 #include <mutex>
 #include <condition_variable>
 #include <functional>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <chrono>
 #include <cstdlib>
 
@@ -410,6 +412,7 @@ extern "C" int hmy_set_params(hmy_ctx* ctx, const float* Pr_b, const float* thet
 
 // ---- host-side helpers of the upload / download paths ------------------------------------------------------------
 static int host_threads() { const unsigned hc = std::thread::hardware_concurrency(); return (int)std::max(1u, std::min(16u, hc ? hc : 4u)); }
+#define HMY_STAGE_CHUNK ((size_t)16u << 20)
 
 // A few persistent host threads for the copies and index builds of the upload / download paths (creating 16
 // threads per 16 MB chunk cost more than the copy itself: 200 MB moved at 7 GB/s).  Process-wide, created on first use.
@@ -453,7 +456,7 @@ static void parallel_ranges(long long n, int T, F fn) {
 }
 
 static int ensure_stage(hmy_ctx* ctx) {
-    constexpr size_t CHUNK = 16u << 20;
+    constexpr size_t CHUNK = HMY_STAGE_CHUNK;
     if (!ctx->h_stage[0])
         for (int i = 0; i < 2; ++i) { CK(cudaMallocHost((void**)&ctx->h_stage[i], CHUNK)); CK(cudaEventCreateWithFlags(&ctx->ev_stage[i], cudaEventDisableTiming)); }
     return 0;
@@ -462,7 +465,7 @@ static int ensure_stage(hmy_ctx* ctx) {
 // pageable host memory -> device through the two pinned bounce buffers: the host copy of chunk i + 1 (spread over
 // threads) overlaps the DMA of chunk i (a plain cudaMemcpy from pageable memory stages single-threaded inside the driver)
 static int h2d_staged(hmy_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
-    constexpr size_t CHUNK = 16u << 20;
+    constexpr size_t CHUNK = HMY_STAGE_CHUNK;
     if (ensure_stage(ctx)) return 1;
     const unsigned char* src8 = (const unsigned char*)src_host; unsigned char* dst8 = (unsigned char*)dst_dev;
     const size_t nchunk = (bytes + CHUNK - 1) / CHUNK;
@@ -1019,7 +1022,7 @@ extern "C" int hmy_ridge_correct(hmy_ctx* ctx) {
         void* args[] = {&s, &what, &mode};
         if (launch(ctx, (const void*)k_tables, dim3(1), dim3(HMY_THREADS), args, 0, false)) return 1;
     }
-    if (split_zcos(ctx)) return 1;           // the round kernel's operand rows follow the new Z_cos
+    if (!ctx->ridge_mma && split_zcos(ctx)) return 1;   // operand rows of the round kernel follow the new Z_cos (the tensor-core apply pass writes them itself)
     if (timer_end(ctx, ctx->ev_ridge)) return 1;
     ctx->ridge_passes++;
     return 0;
@@ -1042,7 +1045,7 @@ static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_o
     CK(cudaGetLastError());
     // device -> pinned bounce buffer -> caller's (pageable, usually untouched) array, double buffered:
     // the DMA of chunk i+1 overlaps the host copy (and first-touch page faults) of chunk i
-    constexpr size_t CHUNK = 16u << 20;
+    constexpr size_t CHUNK = HMY_STAGE_CHUNK;
     if (ensure_stage(ctx)) return 1;
     const unsigned char* src8 = reinterpret_cast<const unsigned char*>(ctx->d_tmp);
     unsigned char* dst8 = reinterpret_cast<unsigned char*>(host_out);

@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(128 * WN) k_ridge_apply_mma(HmyDev st, const f
     float wscale;
     { int e; const float wm = fmaxf(__ldg(wmax_ptr), 1e-30f); frexpf(wm, &e); wscale = ldexpf(1.0f, 13 - e); }
     const float cinv = 1.0f / (HMY_OPSCALE * wscale);
+    const int zs_pairs = 8 * ((st.d + 15) >> 4);                  // u32 (= PC pairs) per hi / lo part of a Zs16 row
+    unsigned int* const zs_rows = reinterpret_cast<unsigned int*>(st.Zs16);
     for (int i = tid; i < HMY_MT * ZSH; i += NTHR) reinterpret_cast<unsigned int*>(Zh)[i] = 0u;
     for (int i = tid; i < HMY_MT * RSH; i += NTHR) reinterpret_cast<unsigned int*>(Rh)[i] = 0u;
     for (int i = tid; i < dpa * RSH; i += NTHR) reinterpret_cast<unsigned int*>(Wh)[i] = 0u;       // Wh and Wl
@@ -310,6 +312,11 @@ __global__ void __launch_bounds__(128 * WN) k_ridge_apply_mma(HmyDev st, const f
                         *reinterpret_cast<unsigned int*>(Zl + (row0 + g) * ZSH + j) = l0;
                         *reinterpret_cast<unsigned int*>(Zh + (row0 + g + 8) * ZSH + j) = h1;
                         *reinterpret_cast<unsigned int*>(Zl + (row0 + g + 8) * ZSH + j) = l1;
+                        // the same split values are the operand rows of the tensor-memory round kernel (hmy_common.cuh: Zs16)
+                        if (st.Zs16 != nullptr && j < 2 * zs_pairs) {
+                            if (v0) { zs_rows[(size_t)(base + row0 + g) * (2 * zs_pairs) + (j >> 1)] = h0; zs_rows[(size_t)(base + row0 + g) * (2 * zs_pairs) + zs_pairs + (j >> 1)] = l0; }
+                            if (v1) { zs_rows[(size_t)(base + row0 + g + 8) * (2 * zs_pairs) + (j >> 1)] = h1; zs_rows[(size_t)(base + row0 + g + 8) * (2 * zs_pairs) + zs_pairs + (j >> 1)] = l1; }
+                        }
                     }
                 }
             }
