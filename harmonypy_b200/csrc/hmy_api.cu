@@ -49,6 +49,7 @@ struct hmy_ctx {
     // limits hold.  want_tc5: -1 auto (default), 0 off, 1 required (unsupported shapes fail)
     int want_tc5 = -1;
     bool tc5_ok = false;                    // shape supported (decided in plan_round)
+    bool legacy_ok = true;                  // the mma.sync / SIMT round kernels fit (their K x B tables live in shared memory)
     bool t5_state = false;                  // the device tables (running O, removed sums) were produced by that kernel
     int tc5_nc = 0, smem_tc5 = 0, G_tc5 = 0;
     const void* fn_tc5 = nullptr; const void* fn_tc5_multi = nullptr;
@@ -264,9 +265,17 @@ static int create_impl(hmy_ctx* ctx, int device, int64_t n_local, int64_t n_glob
     // ridge launch shapes
     ctx->smem_mom = ridge_smem_plan(K, st.KS, ctx->JPW, false).total;
     ctx->smem_apply = ridge_smem_plan(K, st.KS, ctx->JPW, true).total;
-    ctx->smem_solve = (int)(((size_t)(B + 1) * (B + 1 + d) + (B + 1)) * sizeof(double));
-    if (ctx->smem_solve > 200 * 1024) FAIL("ridge system too large for shared memory ((B+1)*(B+1+d) doubles > 200 KB)");
-    CK(cudaFuncSetAttribute((const void*)k_ridge_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_solve));
+    {
+        const size_t per = (size_t)(B + 1) * (B + 1 + d) + (B + 1);
+        if (per * sizeof(double) > 200 * 1024) {
+            // many batch levels: the K augmented systems go to a global work area instead of shared memory
+            if (dev_alloc(ctx, &st.solve_scratch, (size_t)K * per)) return 1;
+            ctx->smem_solve = 0;
+        } else {
+            ctx->smem_solve = (int)(per * sizeof(double));
+            CK(cudaFuncSetAttribute((const void*)k_ridge_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_solve));
+        }
+    }
     return 0;
 }
 
@@ -318,14 +327,19 @@ static int plan_round(hmy_ctx* ctx) {
     if (ctx->want_mma) bind_mma(ctx);
     ctx->smem_round = ctx->use_mma ? mma_smem_plan(st.d, st.K, st.KS, st.B, st.V, nblk, ctx->WN, ctx->NT).total
                                    : round_smem_plan(st.dp, st.KS, st.B, st.V, nblk, ctx->JPW).total;
-    if (ctx->smem_round > 227 * 1024) FAIL("round kernel needs more than 227 KB of shared memory for this (K, B, d, block_size)");
-    CK(cudaFuncSetAttribute(ctx->fn_round, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
-    if (ctx->use_mma) CK(cudaFuncSetAttribute(ctx->fn_round_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
-    CK(cudaFuncSetAttribute(ctx->fn_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
-    int nb = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, ctx->round_threads, ctx->smem_round));
-    if (nb < 1) FAIL("round kernel does not fit on an SM");
-    ctx->G = nb * ctx->sms;
+    // these kernels keep two K x B tables per CTA in shared memory: with hundreds of batch levels they do not fit, and
+    // only the tensor-memory kernel (no K x B tables on chip) can run such a problem -- decided when a stage is launched
+    ctx->legacy_ok = ctx->smem_round <= 227 * 1024;
+    ctx->G = ctx->sms;
+    if (ctx->legacy_ok) {
+        CK(cudaFuncSetAttribute(ctx->fn_round, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
+        if (ctx->use_mma) CK(cudaFuncSetAttribute(ctx->fn_round_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
+        CK(cudaFuncSetAttribute(ctx->fn_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_round));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ctx->fn_round, ctx->round_threads, ctx->smem_round));
+        if (nb < 1) FAIL("round kernel does not fit on an SM");
+        ctx->G = nb * ctx->sms;
+    }
     ctx->tc5_ok = false;
     if (ctx->want_tc5 != 0) {
         const bool shape = st.K <= 128 && st.d <= 64 && nblk <= 32 && st.B <= 65535 && st.Zs16 != nullptr;
@@ -805,6 +819,8 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
         ctx->have_init = true;
         return fetch_obj_tc5(ctx, obj);
     }
+    if (!ctx->legacy_ok) FAIL("this (K, B, d, block_size) needs the tensor-memory round kernel (K <= 128, d <= 64, <= 32 blocks; single GPU or "
+                              "fused exchange): the other round kernels keep K x B tables in shared memory and do not fit");
     ctx->t5_state = false; ctx->r_valid = true;
     CK(cudaMemsetAsync(ctx->zero_round, 0, ctx->zero_round_bytes, ctx->stream));     // obj | Ofresh | Yacc | Told | Dnew
     if (timer_begin(ctx, ctx->ev_init)) return 1;

@@ -57,6 +57,7 @@ struct HmyDev {
     double* Mom;             // [B+1][K][dp]
     float* W;                // [B][K][dp]
     float* wmax;             // max |W| of the last solve
+    double* solve_scratch;   // [K][(B+1)(B+1+d) + B+1] work area of the ridge solve when it does not fit in shared memory (else nullptr)
     // grid barrier
     unsigned int* bar_count; unsigned int* bar_gen;
     // optional per-CTA timeline (globaltimer ns), [grid][HMY_TRACE_SLOTS]; nullptr = off

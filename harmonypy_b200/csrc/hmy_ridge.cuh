@@ -144,7 +144,9 @@ __global__ void __launch_bounds__(HMY_THREADS) k_ridge_moments(HmyDev st) {
 __global__ void __launch_bounds__(128) k_ridge_solve(HmyDev st) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int k = blockIdx.x, n = st.B + 1, d = st.d, m = n + d;
-    double* A = (double*)smem;               // [n][m]
+    // the augmented system lives in shared memory, or -- hundreds of batch levels -- in this cluster's slice of a global
+    // work area (same algorithm; the solve is off the hot path: K small systems per Harmony iteration)
+    double* A = st.solve_scratch ? st.solve_scratch + (size_t)k * ((size_t)n * m + n) : (double*)smem;     // [n][m]
     double* fac = A + (size_t)n * m;         // [n]
     __shared__ int s_piv;
     __shared__ double s_rowsum;

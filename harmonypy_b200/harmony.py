@@ -143,6 +143,23 @@ def prepare_problem(data_mat, meta_data, vars_use, theta=None, lamb=None, sigma=
                    lamb=lamb, lambda_estimation=lambda_estimation, sigma=sigma, K=nclust), vars_use
 
 
+# Shape limits of the CUDA engine (include/harmony_b200.h, "Limits"); the reference has none, so a run that exceeds
+# one fails here with the reason instead of deep inside the library.
+ENGINE_LIMITS = dict(max_d=128, max_K=256, max_covariates=8, max_blocks=250)
+
+
+def check_engine_limits(problem, block_size):
+    lim = ENGINE_LIMITS
+    if problem.d > lim["max_d"]:
+        raise ValueError(f"harmonypy_b200 supports at most {lim['max_d']} PCs (got {problem.d})")
+    if not 2 <= problem.K <= lim["max_K"]:
+        raise ValueError(f"harmonypy_b200 supports 2..{lim['max_K']} clusters (nclust = {problem.K})")
+    if len(problem.levels) > lim["max_covariates"]:
+        raise ValueError(f"harmonypy_b200 supports at most {lim['max_covariates']} batch covariates (got {len(problem.levels)})")
+    if not 0 < block_size <= 1 or int(np.ceil(1.0 / block_size)) > lim["max_blocks"]:
+        raise ValueError(f"block_size must be in [{1.0 / lim['max_blocks']}, 1] (got {block_size})")
+
+
 def get_device(device=None):
     """harmony.py:35-46, restricted to CUDA: returns the CUDA device index."""
     if device is None:
@@ -184,7 +201,7 @@ class Comm:
         return arr
 
     def allreduce_devptr(self, ptr, count, dtype, stream):
-        """In-place sum of `count` elements at device pointer `ptr` (nccl)."""
+        """In-place sum of `count` elements at device pointer `ptr` (nccl), ordered on the engine's `stream`."""
         import torch
 
         class _Mem:
@@ -193,7 +210,10 @@ class Comm:
         m.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f4" if dtype == 0 else "<f8",
                                       "data": (int(ptr), False), "version": 2}
         t = torch.as_tensor(m, device="cuda")
-        self.dist.all_reduce(t, group=self.group)
+        # the engine's kernels run on `stream`: the collective must be enqueued there too, whatever stream the
+        # caller has made current in the meantime
+        with torch.cuda.stream(torch.cuda.ExternalStream(int(stream)) if stream else torch.cuda.current_stream()):
+            self.dist.all_reduce(t, group=self.group)
         return 0
 
     def broadcast_array(self, arr, src=0):
@@ -204,12 +224,14 @@ class Comm:
         self.dist.broadcast(t, src=src, group=self.group)
         return t.cpu().numpy()
 
-    def gather_rows(self, local, N):
-        """All ranks' row blocks -> the full matrix on every rank."""
+    def gather_rows(self, local, N, lo=None):
+        """All ranks' row blocks -> the full matrix on every rank.  lo: first global row of this rank's block
+        (default: the even split of shard(); pre-sharded inputs pass their own offset)."""
         import torch
         out = np.zeros((N,) + local.shape[1:], dtype=local.dtype)
-        lo, hi = self.shard(N)
-        out[lo:hi] = local
+        if lo is None:
+            lo = self.shard(N)[0]
+        out[lo:lo + local.shape[0]] = local
         t = torch.from_numpy(out)
         if self.backend == "nccl":
             t = t.cuda()
@@ -325,6 +347,8 @@ class Harmony:
         self.kmeans_rounds = []
         self._last_obj = None
 
+        if engine_factory is None:
+            check_engine_limits(problem, block_size)
         factory = engine_factory or _cuda_engine_factory
         self._engine = factory(problem, self._lo, self._hi, device, comm, engine_options)
         if perm_mode == "device" and "seed" not in (engine_options or {}):
@@ -365,7 +389,7 @@ class Harmony:
         local = self._engine.get(which)
         if self.comm is None or self.comm.world == 1:
             return local
-        return self.comm.gather_rows(local, self.N)
+        return self.comm.gather_rows(local, self.N, self._lo)
 
     @property
     def Z_corr(self):
@@ -406,12 +430,17 @@ class Harmony:
     def Phi(self):
         """One-hot batch indicators (N x B), materialised on demand  -- harmony.py:323-326."""
         p = self.problem
-        out = np.zeros((self.N, self.B), dtype=np.float32)
+        n_loc = p.codes.shape[1]
+        out = np.zeros((n_loc, self.B), dtype=np.float32)
         off = 0
-        rows = np.arange(self.N)
+        rows = np.arange(n_loc)
         for v in range(len(p.levels)):
             out[rows, off + p.codes[v]] = 1
             off += int(p.levels[v])
+        if n_loc != self.N:                                       # pre-sharded input: this rank holds its own rows only
+            if self.comm is None:
+                raise ValueError("Phi: the problem holds a shard of the cells but no communicator was given")
+            return self.comm.gather_rows(out, self.N, self._lo)
         return out
 
     @property

@@ -19,6 +19,12 @@
  *     K x B (row stride B) like the reference's properties (harmony.py:313-321);
  *   - B = sum(levels_per_var) one-hot rows in pd.get_dummies order (harmony.py:133):
  *     covariate-major, level-minor.  Level codes are 0-based within their covariate.
+ *
+ * Limits (the reference has none; hmy_create / hmy_set_params fail with the reason, the Python host checks them first):
+ *   d <= 128 PCs, 2 <= K <= 256 clusters, <= 8 batch covariates, <= 250 blocks (block_size >= 0.004), B <= 65535 levels.
+ *   The tensor-memory round kernel (K <= 128, d <= 64, <= 32 blocks) has no limit on B; the other round kernels keep
+ *   two K x B tables per CTA in shared memory (about 250 levels at K = 100) and fail beyond that.
+ *   hmy_lisi_compute: 3 * perplexity <= 128 neighbours.
  */
 #ifndef HARMONY_B200_H
 #define HARMONY_B200_H
@@ -123,6 +129,8 @@ int hmy_synchronize(hmy_ctx* ctx);
  *                      the 4K bytes per cell; hmy_ridge_correct and hmy_get(HMY_R) fail until a stage ran with 1
  *   "relaxed"    0/1   fused multi-GPU mode: exchange the K x B table once per round instead of once
  *                      per block (NOT exact; default 0)
+ *   "dbg"        bits  timing experiments on the tensor-memory round kernel (skips parts of its work: results are WRONG
+ *                      when non-zero; default 0; scripts/gpu_dbg.sh)
  *   "timing"     0/1   CUDA-event timers around the stages (default 1)
  *   "reset"      1     back to the state right after hmy_set_data (benchmark restarts)
  *   "trace"      1     per-CTA timeline of the round kernel, read with hmy_get(HMY_TRACE) */

@@ -185,6 +185,8 @@ def _oracle_for(prob, dtype=np.float64, **kw):
     (257, 4, [2], 5, {}),                         # tiny: fewer cells than CTAs
     (6000, 72, [3, 2], 40, {}),                   # d > 64: fp32 SIMT round + ridge kernels (fallback path)
     (4000, 64, [4], 130, {}),                     # d = 64: tensor-core round, SIMT ridge (no spare PC column); K > 128
+    (30000, 20, [400], 100, {}),                  # hundreds of batch levels: only the tensor-memory kernel fits (no K x B tables
+                                                  # on chip), ridge solve in its global work area
 ])
 def test_one_iteration_against_fp64_oracle(N, d, levels, K, kw):
     """init + 3 rounds + ridge on fresh synthetic data, every stage against the fp64 oracle."""
