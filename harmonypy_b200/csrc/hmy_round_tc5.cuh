@@ -546,15 +546,41 @@ __device__ __forceinline__ float t5_ll_read(const uint2* p, unsigned int seq) {
     }
     return __uint_as_float(v.x);
 }
+// sum over the W sources of one LL element (p: source 0's packet, stride: packets between sources), in rank order.
+// All W loads are issued before the first sequence number is looked at (one round trip when the data is there, which
+// is the usual case: a dependent poll per source cost W round trips -- measured 8 us per block at 8 GPUs).
+static __device__ __noinline__ float t5_ll_sum(const uint2* p, size_t stride, int W, unsigned int seq) {
+    uint2 v[HMY_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < HMY_MAX_WORLD; ++r) if (r < W) v[r] = ld_volatile_v2(p + (size_t)r * stride);
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < HMY_MAX_WORLD; ++r)
+        if (r < W) s += (v[r].y == seq) ? __uint_as_float(v[r].x) : t5_ll_read(p + (size_t)r * stride, seq);
+    return s;
+}
+// the same for a double that travels as two packets (low word, high word)
+static __device__ __noinline__ double t5_ll_sum_d(const uint2* p, size_t stride, int W, unsigned int seq) {
+    uint2 lo[HMY_MAX_WORLD], hi[HMY_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < HMY_MAX_WORLD; ++r) if (r < W) { lo[r] = ld_volatile_v2(p + (size_t)r * stride); hi[r] = ld_volatile_v2(p + (size_t)r * stride + 1); }
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < HMY_MAX_WORLD; ++r)
+        if (r < W) {
+            const unsigned int l = (lo[r].y == seq) ? lo[r].x : __float_as_uint(t5_ll_read(p + (size_t)r * stride, seq));
+            const unsigned int h = (hi[r].y == seq) ? hi[r].x : __float_as_uint(t5_ll_read(p + (size_t)r * stride + 1, seq));
+            s += __longlong_as_double((long long)(((unsigned long long)h << 32) | l));
+        }
+    return s;
+}
 // element e of this launch's Dnew[i], summed over ranks
 template <bool MULTI>
 __device__ __forceinline__ float t5_dnew(const HmyDev& st, int i, size_t e) {
     const size_t nD = t5_nD(st);
     if (!MULTI) return __ldcg(&st.Dnew[(size_t)i * nD + e]);
     const uint2* base = reinterpret_cast<const uint2*>(st.xpeer[st.xrank] + st.x5_off_d) + ((size_t)(st.x5_seq & 1u) * st.nblk + i) * HMY_MAX_WORLD * nD + e;
-    float s = 0.f;
-    for (int r = 0; r < st.xworld; ++r) s += t5_ll_read(base + (size_t)r * nD, st.x5_seq);
-    return s;
+    return t5_ll_sum(base, nD, st.xworld, st.x5_seq);
 }
 // after the rank's barrier: this CTA's slice of Dnew[blk] goes to every rank
 __device__ __forceinline__ void t5_push_block(const HmyDev& st, int blk, unsigned int G) {
@@ -1001,11 +1027,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
                         // the next round's removed sums, summed over ranks (this CTA's slice; rank order: identical everywhere)
                         const long long e0 = (long long)blockIdx.x * (long long)nT / G, e1 = (long long)(blockIdx.x + 1) * (long long)nT / G;
                         const uint2* src = reinterpret_cast<const uint2*>(st.xpeer[me] + st.x5_off_t) + (size_t)par * HMY_MAX_WORLD * nT;
-                        for (long long e = e0 + tid; e < e1; e += T5_EPI_THREADS) {
-                            float sum = 0.f;
-                            for (int r = 0; r < W; ++r) sum += t5_ll_read(src + (size_t)r * nT + (size_t)e, seq);
-                            st.Told_next[e] = sum;
-                        }
+                        for (long long e = e0 + tid; e < e1; e += T5_EPI_THREADS) st.Told_next[e] = t5_ll_sum(src + (size_t)e, nT, W, seq);
                     }
                 }
                 break;
@@ -1021,13 +1043,18 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         const int n = (int)nBK;
         const int e0 = (int)((long long)blockIdx.x * n / G), e1 = (int)((long long)(blockIdx.x + 1) * n / G);
         double part = 0.0;
-        for (int e = e0 + tid; e < e1; e += T5_EPI_THREADS) {
+        // one warp per element, lane = block: the per-block terms (with several GPUs: W polled packets each) are read
+        // side by side instead of one after the other
+        for (int e = e0 + warp; e < e1; e += T5_EPI_WARPS) {
             const int b = e / st.K, k = e - b * st.K;
-            double o = 0.0, rs = 0.0;
-            for (int i = 0; i < nblocks; ++i) { o += (double)t5_dnew<MULTI>(st, i, (size_t)e); rs += (double)t5_dnew<MULTI>(st, i, nBK + k); }
-            st.O[e] = o;
-            const float oc = fmaxf((float)o, 1e-8f), ec = fmaxf((float)(rs * (double)st.Pr_b[b]), 1e-8f);
-            part += (double)st.sigma[k] * (double)st.theta[b] * (double)logf((oc + ec) / ec) * o;
+            double o = (lane < nblocks) ? (double)t5_dnew<MULTI>(st, lane, (size_t)e) : 0.0;
+            double rs = (lane < nblocks) ? (double)t5_dnew<MULTI>(st, lane, nBK + k) : 0.0;
+            o = warp_sum_d(o); rs = warp_sum_d(rs);
+            if (lane == 0) {
+                st.O[e] = o;
+                const float oc = fmaxf((float)o, 1e-8f), ec = fmaxf((float)(rs * (double)st.Pr_b[b]), 1e-8f);
+                part += (double)st.sigma[k] * (double)st.theta[b] * (double)logf((oc + ec) / ec) * o;
+            }
         }
         if (!MULTI) {
             part = warp_sum_d(part);
@@ -1049,18 +1076,8 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
             } else {
                 const size_t nY = (size_t)st.K * st.dp + 2;
                 const uint2* src = reinterpret_cast<const uint2*>(st.xpeer[st.xrank] + st.x5_off_y) + (size_t)(st.x5_seq & 1u) * HMY_MAX_WORLD * 2 * nY;
-                for (int r = 0; r < st.xworld; ++r) {
-                    if (lane < st.d) {
-                        const uint2* pz = src + (size_t)r * 2 * nY + 2 * ((size_t)k * st.dp + lane);
-                        const unsigned long long lo = __float_as_uint(t5_ll_read(pz, st.x5_seq)), hi = __float_as_uint(t5_ll_read(pz + 1, st.x5_seq));
-                        y0 += __longlong_as_double((long long)((hi << 32) | lo));
-                    }
-                    if (lane + 32 < st.d) {
-                        const uint2* pz = src + (size_t)r * 2 * nY + 2 * ((size_t)k * st.dp + lane + 32);
-                        const unsigned long long lo = __float_as_uint(t5_ll_read(pz, st.x5_seq)), hi = __float_as_uint(t5_ll_read(pz + 1, st.x5_seq));
-                        y1 += __longlong_as_double((long long)((hi << 32) | lo));
-                    }
-                }
+                if (lane < st.d) y0 = t5_ll_sum_d(src + 2 * ((size_t)k * st.dp + lane), 2 * nY, st.xworld, st.x5_seq);
+                if (lane + 32 < st.d) y1 = t5_ll_sum_d(src + 2 * ((size_t)k * st.dp + lane + 32), 2 * nY, st.xworld, st.x5_seq);
             }
             const double inv = 1.0 / sqrt(warp_sum_d(y0 * y0 + y1 * y1));
             if (lane < st.dp) st.Ynext[(size_t)k * st.dp + lane] = (lane < st.d) ? (float)(y0 * inv) : 0.f;
@@ -1070,12 +1087,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
             // objective sums over all ranks (rank order) for the host
             const size_t nY = (size_t)st.K * st.dp + 2;
             const uint2* src = reinterpret_cast<const uint2*>(st.xpeer[st.xrank] + st.x5_off_y) + (size_t)(st.x5_seq & 1u) * HMY_MAX_WORLD * 2 * nY;
-            double sum = 0.0;
-            for (int r = 0; r < st.xworld; ++r) {
-                const uint2* pz = src + (size_t)r * 2 * nY + 2 * (nY - 2 + tid);
-                const unsigned long long lo = __float_as_uint(t5_ll_read(pz, st.x5_seq)), hi = __float_as_uint(t5_ll_read(pz + 1, st.x5_seq));
-                sum += __longlong_as_double((long long)((hi << 32) | lo));
-            }
+            const double sum = t5_ll_sum_d(src + 2 * (nY - 2 + tid), 2 * nY, st.xworld, st.x5_seq);
             st.obj_out[tid] = sum;
         }
     }
