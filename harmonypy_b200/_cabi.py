@@ -32,6 +32,7 @@ SYMBOLS = {
     "hmy_kmeans_init": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_double, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_kmeans_round": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_queue_perm": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hmy_objectives": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "hmy_ridge_correct": (C.c_int, [C.c_void_p]),
     "hmy_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "hmy_synchronize": (C.c_int, [C.c_void_p]),
@@ -71,6 +72,38 @@ def load():
 
 def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+class _ResultPool:
+    """Host buffers for the large result reads (Z_corr, R ...).  A fresh NumPy array costs one page fault per 4 KB on
+    its first write -- measured: 20-40 ms of a 200 MB read-back -- so buffers whose arrays have been dropped are handed
+    out again.  A buffer is free when nothing but the pool refers to it (the arrays returned to callers are views whose
+    `base` is the buffer, so it cannot be reused while any of them -- or a slice of them -- is alive)."""
+    MAX_PER_SIZE = 3
+    MIN_BYTES = 8 << 20
+
+    def __init__(self):
+        self._bufs = {}
+
+    def array(self, shape, dtype):
+        import sys
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        if nbytes < self.MIN_BYTES:
+            return np.empty(shape, dtype=dtype)
+        lst = self._bufs.setdefault(nbytes, [])
+        owner = None
+        for b in lst:
+            if sys.getrefcount(b) == 3:          # the list, the loop variable, getrefcount's argument: no view alive
+                owner = b
+                break
+        if owner is None:
+            owner = np.empty(nbytes, dtype=np.uint8)
+            if len(lst) < self.MAX_PER_SIZE:
+                lst.append(owner)
+        return owner.view(dtype).reshape(shape)
+
+
+_POOL = _ResultPool()
 
 
 class Engine:
@@ -145,8 +178,9 @@ class Engine:
                  "hmy_kmeans_init")
         return Y, {"iterations": int(info[0]), "inertia": float(info[1]), "last_shift2": float(info[2])}
 
-    def kmeans_round(self, perm=None):
-        obj = (C.c_double * 3)()
+    def kmeans_round(self, perm=None, wait=True):
+        """One round.  wait=False (lookahead contexts): enqueue it and return None; read the sums with objectives()."""
+        obj = (C.c_double * 3)() if wait else None
         if perm is None:
             p = None
         else:
@@ -154,7 +188,13 @@ class Engine:
             assert perm.shape == (self.n_global,)
             p = _ptr(perm)
         self._ck(self.lib.hmy_kmeans_round(self.h, p, obj), "hmy_kmeans_round")
-        return obj[0], obj[1], obj[2]
+        return (obj[0], obj[1], obj[2]) if wait else None
+
+    def objectives(self, n):
+        """Objective sums of the last n stages, oldest first (waits for the stream once)."""
+        out = (C.c_double * (3 * n))()
+        self._ck(self.lib.hmy_objectives(self.h, int(n), out), "hmy_objectives")
+        return [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(n)]
 
     @property
     def lookahead(self):
@@ -181,7 +221,7 @@ class Engine:
             R: ((n, K), np.float32), Y: ((K, d), np.float32), O: ((K, B), np.float64), E: ((K, B), np.float64),
             W: ((B, K, d), np.float32),
         }[which]
-        out = np.empty(shape, dtype=dt)
+        out = _POOL.array(shape, dt)
         self._ck(self.lib.hmy_get(self.h, int(which), _ptr(out), out.nbytes), "hmy_get")
         return out
 

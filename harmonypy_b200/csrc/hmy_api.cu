@@ -62,6 +62,8 @@ struct hmy_ctx {
     unsigned long long bar_count64 = 0;     // host mirror of the device grid-barrier counter
     long long n_assigned = 0, n_done = 0;   // rounds (since init) with a block assignment / executed
     int write_r = 1; bool r_valid = true;   // R rows in HBM are those of the last stage
+    double* objring = nullptr;              // [16][4] objective sums of the last stages (tc5 path), [16][2] all-rank sums behind them
+    long long stages_launched = 0;          // tc5 stages launched so far (ring slot = stages_launched % 16)
     int G = 0, sms = 0;
     int smem_round = 0, smem_mom = 0, smem_apply = 0, smem_solve = 0;
     int grid_ridge = 0, grid_mom = 0, ridge_threads = HMY_THREADS;
@@ -363,6 +365,7 @@ static int plan_round(hmy_ctx* ctx) {
                 if (dev_alloc(ctx, &ctx->t5_rsum[i], (size_t)st.K)) return 1;
             }
             if (dev_alloc(ctx, &ctx->t5_dnew, ctx->t5_table_floats)) return 1;
+            if (dev_alloc(ctx, &ctx->objring, (size_t)16 * 6)) return 1;
             ctx->tc5_ok = true;
         }
     }
@@ -759,6 +762,12 @@ static int launch_tc5(hmy_ctx* ctx, int mode) {
     s.Rsum = ctx->t5_rsum[ctx->rsum_cur]; s.Rsum_next = ctx->t5_rsum[ctx->rsum_cur ^ 1];
     s.Dnew = ctx->t5_dnew;
     s.write_R = ctx->write_r;
+    {   // every stage leaves its objective sums in its own ring slot: rounds can be launched back to back and read later
+        const int slot = (int)(ctx->stages_launched % 16);
+        s.obj = ctx->objring + 4 * slot; s.obj_out = ctx->objring + 64 + 2 * slot;
+        CK(cudaMemsetAsync(s.obj, 0, 4 * sizeof(double), ctx->stream));
+        CK(cudaMemsetAsync(s.Yacc, 0, (size_t)s.K * s.dp * sizeof(double), ctx->stream));
+    }
     if (mode == 1) { s.blk_next = ctx->blkbuf[0]; s.Told = nullptr; s.Told_next = ctx->t5_told[ctx->told_cur]; }
     else { s.blk = ctx->blkbuf[r & 1]; s.blk_next = ctx->blkbuf[(r + 1) & 1]; }
     unsigned long long base = ctx->bar_count64;
@@ -768,23 +777,39 @@ static int launch_tc5(hmy_ctx* ctx, int mode) {
     ctx->bar_count64 += (unsigned long long)ctx->G_tc5 * (unsigned long long)(mode == 1 ? 1 : s.nblk);
     ctx->r_valid = ctx->write_r != 0;
     ctx->t5_state = true;
+    ctx->stages_launched++;
     return 0;
 }
 
-// objective sums of the last tc5 stage: the kernel leaves them in obj[0..2]
-static int fetch_obj_tc5(hmy_ctx* ctx, double obj[3]) {
-    CK(cudaMemcpyAsync(ctx->h_obj, ctx->st.obj, 4 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    double go[2] = {0.0, 0.0};
-    if (ctx->fused) CK(cudaMemcpyAsync(go, ctx->st.obj_out, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+// objective sums of the last n tc5 stages (oldest first): each stage left them in its ring slot
+static int fetch_obj_tc5_n(hmy_ctx* ctx, int n, double* out3n) {
+    if (n < 1 || n > 16 || n > ctx->stages_launched) FAIL("hmy_objectives: n must be in 1..16 and at most the number of stages run");
+    double h[16 * 6];
+    CK(cudaMemcpyAsync(h, ctx->objring, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (obj) {
+    for (int i = 0; i < n; ++i) {
+        const int slot = (int)((ctx->stages_launched - n + i) % 16);
+        const double* o = h + 4 * slot;
         if (ctx->fused) {
             // sums over all ranks (rank order) and the cross-entropy term in 2^-30 fixed point: identical on every rank
-            long long fx; std::memcpy(&fx, &ctx->h_obj[3], sizeof fx);
-            obj[0] = go[0]; obj[1] = go[1]; obj[2] = (double)fx / 1073741824.0;
-        } else { obj[0] = ctx->h_obj[0]; obj[1] = ctx->h_obj[1]; obj[2] = ctx->h_obj[2]; }
+            long long fx; std::memcpy(&fx, &o[3], sizeof fx);
+            out3n[3 * i] = h[64 + 2 * slot]; out3n[3 * i + 1] = h[64 + 2 * slot + 1]; out3n[3 * i + 2] = (double)fx / 1073741824.0;
+        } else { out3n[3 * i] = o[0]; out3n[3 * i + 1] = o[1]; out3n[3 * i + 2] = o[2]; }
     }
     return 0;
+}
+static int fetch_obj_tc5(hmy_ctx* ctx, double obj[3]) {
+    double o[3];
+    if (fetch_obj_tc5_n(ctx, 1, o)) return 1;
+    if (obj) { obj[0] = o[0]; obj[1] = o[1]; obj[2] = o[2]; }
+    return 0;
+}
+
+extern "C" int hmy_objectives(hmy_ctx* ctx, int n, double* obj_3n) {
+    CK(cudaSetDevice(ctx->device));
+    if (!obj_3n) FAIL("hmy_objectives: NULL output");
+    if (!use_tc5(ctx) || !ctx->t5_state) FAIL("hmy_objectives: only contexts with counter \"lookahead\" = 1 keep the objective sums of past rounds");
+    return fetch_obj_tc5_n(ctx, n, obj_3n);
 }
 
 // ---- a2: init ------------------------------------------------------------------------------
@@ -808,7 +833,6 @@ extern "C" int hmy_init_from_centroids(hmy_ctx* ctx, const float* Y0, double obj
         ctx->n_done = 0;
         if (ctx->n_assigned == 0) { if (assign_round(ctx, nullptr, 0)) return 1; }     // device permutation
         else if (ctx->n_assigned != 1) FAIL("hmy_init_from_centroids: more than one permutation queued");
-        CK(cudaMemsetAsync(ctx->zero_round, 0, (4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double), ctx->stream));   // obj | Ofresh | Yacc
         CK(cudaMemsetAsync(ctx->t5_dnew, 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
         CK(cudaMemsetAsync(ctx->t5_told[ctx->told_cur], 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
         if (timer_begin(ctx, ctx->ev_init)) return 1;
@@ -938,7 +962,6 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
             ctx->launches += 3;
             CK(cudaGetLastError());
         }
-        CK(cudaMemsetAsync(ctx->zero_round, 0, (4 + (size_t)st.B * st.K + (size_t)st.K * st.dp) * sizeof(double), ctx->stream));   // obj | Ofresh | Yacc
         CK(cudaMemsetAsync(ctx->t5_dnew, 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
         CK(cudaMemsetAsync(ctx->t5_told[ctx->told_cur ^ 1], 0, ctx->t5_table_floats * sizeof(float), ctx->stream));
         if (timer_begin(ctx, ctx->ev_round)) return 1;
@@ -948,6 +971,7 @@ extern "C" int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double o
         ctx->n_done++;
         swap_centroids(ctx);
         ctx->rounds++;
+        if (!obj) return 0;                  // the caller reads the sums later (hmy_objectives): no host round trip now
         return fetch_obj_tc5(ctx, obj);
     }
     // block of every cell for this round (harmony.py:471-475)

@@ -561,10 +561,24 @@ class Harmony:
         """harmony.py:437-462."""
         rounds = 0
         lazy = getattr(self, "_lazy_R", False)
+        pending = 0            # rounds enqueued whose objective has not been read yet
         for i in range(self.max_iter_kmeans):
+            can_stop = i > self.window_size or i == self.max_iter_kmeans - 1
             if lazy:      # R must be in HBM after every round the loop can end with
-                self._engine.set_option("write_r", int(i > self.window_size or i == self.max_iter_kmeans - 1))
-            self.kmeans_round()
+                self._engine.set_option("write_r", int(can_stop))
+            if lazy and not can_stop:
+                # the convergence rule cannot fire after this round (harmony.py:455): no host round trip, the
+                # objective is read together with the next one that matters
+                self._engine.kmeans_round(self._next_perm(), wait=False)
+                pending += 1
+            else:
+                if pending:
+                    self._engine.kmeans_round(self._next_perm(), wait=False)
+                    for o in self._engine.objectives(pending + 1):
+                        self._record_objective(o)
+                    pending = 0
+                else:
+                    self.kmeans_round()
             rounds = i + 1
             if i > self.window_size and self.check_convergence(0):    # :455-458
                 break

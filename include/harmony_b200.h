@@ -97,6 +97,12 @@ int hmy_kmeans_init(hmy_ctx* ctx, uint64_t seed, int max_iter, double tol, float
  * device-side pseudo-random permutation from (seed, round counter). */
 int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double obj[3]);
 
+/* Contexts with counter "lookahead" = 1: hmy_kmeans_round(ctx, perm, NULL) enqueues the round without waiting for its
+ * objective sums, so that the rounds whose objective cannot stop the loop yet (harmony.py:455-458: the first four of a
+ * cluster() call) run back to back with no host round trip in between; hmy_objectives then waits once and returns the
+ * sums of the last n stages (oldest first, 3 doubles each, n <= 16).  With "lookahead" = 0 obj must not be NULL. */
+int hmy_objectives(hmy_ctx* ctx, int n, double* obj_3n);
+
 /* Contexts whose counter "lookahead" is 1 (single-GPU persistent runs on the tensor-memory round kernel) run the
  * block permutations ONE ROUND AHEAD: a round already accumulates, per block of the NEXT round, the sums that round
  * will remove from O (harmony.py:491-492), so it must know the next round's blocks.  Call order there:
