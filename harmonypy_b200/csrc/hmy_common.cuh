@@ -21,7 +21,7 @@
 #define HMY_CPW 8            // cells per warp inside a tile (HMY_TILE / HMY_WARPS)
 #define HMY_MAX_V 8
 #define HMY_MAX_NBLK 250
-#define HMY_TRACE_SLOTS 192
+#define HMY_TRACE_SLOTS 256
 #define HMY_MAX_WORLD 8
 #define HMY_XFLAG_STRIDE 128     // bytes between the per-source flags of an exchange buffer
 #define HMY_XPAYLOAD_OFF 4096
@@ -97,6 +97,19 @@ __device__ __forceinline__ void hmy_trace_any(const HmyDev& st, int slot) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + slot] = t;
+    }
+}
+
+// Longest gap between successive events of one role (one thread calls it): slot `base` holds the last event's time,
+// base + 1 + site the longest gap that ended at `site`, base + 1 + nsites + site where (caller's tag) it happened.
+__device__ __forceinline__ void hmy_trace_gap(const HmyDev& st, int base, int nsites, int site, unsigned long long tag) {
+    if (st.trace != nullptr) {
+        volatile unsigned long long* T = st.trace + (size_t)blockIdx.x * HMY_TRACE_SLOTS;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const unsigned long long prev = T[base];
+        if (prev != 0 && now - prev > T[base + 1 + site]) { T[base + 1 + site] = now - prev; T[base + 1 + nsites + site] = tag; }
+        T[base] = now;
     }
 }
 

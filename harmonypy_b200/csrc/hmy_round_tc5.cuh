@@ -201,14 +201,20 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
     const int nblocks = (mode == 1) ? 1 : st.nblk;
     const unsigned int sbase = smem_u32(smem);
     if (mode != 1) {
-        // The i-th share of every block's position-sorted list lies around the i-th share of the position range: the
-        // combinations there get their slots up front, so that the epilogue follows their running O rows from block 0
-        // (a slot first met in the middle of a round has to catch up on every finished block -- the whole grid waits)
-        const long long c0 = (long long)blockIdx.x * st.N / G, c1 = (long long)(blockIdx.x + 1) * st.N / G, m = (c1 - c0) / 2;
-        const long long probe[4] = {c0, max(c1 - 1, c0), max(c0 - m, 0LL), min(c1 - 1 + m, st.N - 1)};
-        for (int i = 0; i < 4 && st.N > 0; ++i) {
-            const int c = st.combo[probe[i]];
-            if (c == sc0 || c == sc1 || c == sc2 || c == sc3 || nslots == T5_SLOTS) continue;
+        // Every combination this CTA meets in the round gets its slot up front, so that the epilogue follows its running
+        // O rows from block 0: a slot first met in the middle of a round has to catch up on every finished block (measured
+        // 1.1 us per block, 8 us with 8 GPUs -- and the whole grid, on every GPU, waits for that one CTA).  The lists are
+        // sorted by position and positions by combination, so the CTA's share of block b covers the combinations from its
+        // first entry's to its last entry's; lane b looks those two up.
+        int cf = 0x7fffffff, cl = -1;
+        for (int b = lane; b < nblocks; b += 32) {
+            long long lb, le;
+            block_share(st, b, blockIdx.x, G, lb, le);
+            if (le > lb) { cf = min(cf, __ldg(&st.list2[lb]).y >> 8); cl = max(cl, __ldg(&st.list2[le - 1]).y >> 8); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { cf = min(cf, __shfl_xor_sync(0xffffffffu, cf, o)); cl = max(cl, __shfl_xor_sync(0xffffffffu, cl, o)); }
+        for (int c = cf; c <= cl && nslots < T5_SLOTS; ++c) {       // more than four: the tiles evict as they go
             const int slot = nslots++;
             if (slot == 0) sc0 = c; else if (slot == 1) sc1 = c; else if (slot == 2) sc2 = c; else sc3 = c;
             if ((lane >> 3) == slot) mylev = (unsigned short)(((lane & 7) < st.V) ? st.combo_lev[c * st.V + (lane & 7)] : 0);
@@ -237,6 +243,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
                 t5_wait(bacc, (use & 1u) ^ 1u);
             }
             hmy_trace_any(st, psl);
+            if (lane == 0) hmy_trace_gap(st, 184, 3, 0, (unsigned long long)t);
             unsigned char* meta = smem + t5_off_meta(NC) + s * 1024;
             int* mcell = reinterpret_cast<int*>(meta);
             unsigned short* mslot = reinterpret_cast<unsigned short*>(meta + T5_META_SLOTNB);
@@ -318,6 +325,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
             }
             __syncwarp();
             hmy_trace_any(st, psl + 1);
+            if (lane == 0) hmy_trace_gap(st, 184, 3, 1, (unsigned long long)t);
             // ---- gather: 8 rows x 4 chunks of 16 bytes per instruction (conflict-free core-matrix writes).  Straight-line
             // code: the cell ids of this lane's 16 rows first (one batch of shared-memory loads), then nothing but copies
             {
@@ -350,6 +358,7 @@ __device__ void t5_producer(const HmyDev& st, int mode, unsigned char* smem, uns
                 asm volatile("cp.async.commit_group;" ::: "memory");
             }
             hmy_trace_any(st, psl + 2);
+            if (lane == 0) hmy_trace_gap(st, 184, 3, 2, (unsigned long long)t);
             if (pending) {
                 asm volatile("cp.async.wait_group 1;" ::: "memory");
                 t5_fence_async();
@@ -411,6 +420,7 @@ __device__ void t5_mma_warp(const HmyDev& st, unsigned char* smem, unsigned int 
                 const bool f_lastr = __any_sync(0xffffffffu, (flags_v & T5_F_LAST_ROUND) != 0u);
                 const int tsl = (hdr[T5_H_BLK] == 5 && sc_in_blk < 4 && lane == 0) ? 128 + 4 * sc_in_blk : HMY_TRACE_SLOTS;
                 hmy_trace_any(st, tsl);
+                if (lane == 0) hmy_trace_gap(st, 192, 4, 0, ((unsigned long long)hdr[T5_H_BLK] << 8) | (unsigned long long)sc_in_blk);
                 if (!f_empty) {
                     const unsigned long long dZh = dZK + (unsigned long long)s * STAGE16, dZl = dZh + PART16;
                     const unsigned int dcol = tmem + T5_COL_D1 + 128u * d;
@@ -431,6 +441,7 @@ __device__ void t5_mma_warp(const HmyDev& st, unsigned char* smem, unsigned int 
                 }
                 if (t5_elect()) t5_commit(bar0 + 8u * (T5_B_SFULL + d));
                 hmy_trace_any(st, tsl + 1);
+                if (lane == 0) hmy_trace_gap(st, 192, 4, 1, ((unsigned long long)hdr[T5_H_BLK] << 8) | (unsigned long long)sc_in_blk);
                 sc_in_blk = f_lastb ? 0 : sc_in_blk + 1;
                 if (f_lastr) score_end = true;
                 ++ts;
@@ -452,6 +463,7 @@ __device__ void t5_mma_warp(const HmyDev& st, unsigned char* smem, unsigned int 
             const int blk_v = hdr[T5_H_BLK];
             const int tsl = (blk_v == 5 && ac_in_blk < 4 && lane == 0) ? 130 + 4 * ac_in_blk : HMY_TRACE_SLOTS;
             hmy_trace_any(st, tsl);
+            if (lane == 0) hmy_trace_gap(st, 192, 4, 2, ((unsigned long long)blk_v << 8) | (unsigned long long)ac_in_blk);
             if (f_evict) ot_started = 0u;
             const bool cyc = st.trace != nullptr && blk_v == 5 && ac_in_blk == 0 && lane == 0;
 #define T5_CYC(i_) do { if (cyc) st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + 160 + (i_)] = (unsigned long long)clock64(); } while (0)
@@ -501,6 +513,7 @@ __device__ void t5_mma_warp(const HmyDev& st, unsigned char* smem, unsigned int 
             if (t5_elect()) t5_commit(bar0 + 8u * (T5_B_ACC + s));
             T5_CYC(4);
             hmy_trace_any(st, tsl + 1);
+            if (lane == 0) hmy_trace_gap(st, 192, 4, 3, ((unsigned long long)blk_v << 8) | (unsigned long long)ac_in_blk);
             T5_CYC(5);
             ac_in_blk = f_lastb ? 0 : ac_in_blk + 1;
             ++ta;
@@ -756,6 +769,26 @@ __device__ __forceinline__ void t5_grid_barrier(const HmyDev& st, unsigned long 
 // per tile i of block 5: 102 + 6 i + {0 scores ready, 1 scores in registers, 2 pass 1 done, 3 row sums met,
 // 4 operand tile free, 5 operand tile written}
 #define T5_STAMP(slot_) hmy_trace(st, (slot_))
+// The slowest tile of every CTA (thread 0, all traced launches): slots 166 + {0 tile described, 1 scores ready, 2 scores in
+// registers, 3 pass 1 done, 4 row sums met, 5 operand tile free} are the running tile's stamps; when a tile ends later
+// after its predecessor (or after the block's penalty rows) than any before, they are copied to 176.., with the gap in 174,
+// block << 8 | tile in 175, the end in 182 and the predecessor's end in 183.
+#define T5_WT(i_) hmy_trace(st, 166 + (i_))
+__device__ __forceinline__ void t5_trace_tile_end(const HmyDev& st, int blk, int tile, bool restart) {
+    if (st.trace != nullptr && threadIdx.x == 0) {
+        volatile unsigned long long* T = st.trace + (size_t)blockIdx.x * HMY_TRACE_SLOTS;
+        unsigned long long now;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        const unsigned long long prev = T[173];
+        if (!restart && prev != 0 && now - prev > T[174]) {
+            T[174] = now - prev; T[175] = ((unsigned long long)blk << 8) | (unsigned long long)tile;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) T[176 + i] = T[166 + i];
+            T[182] = now; T[183] = prev;
+        }
+        T[173] = now;
+    }
+}
 template <int NC, bool MULTI>
 __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, unsigned int bar0, unsigned int tmem,
                             unsigned int G, unsigned long long bar_base) {
@@ -783,6 +816,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
     for (;;) {
         const unsigned int s = t % T5_NZ, d = t & 1u;
         t5_wait(bar0 + 8u * (T5_B_ZFULL + s), (t / T5_NZ) & 1u);
+        T5_WT(0);
         const unsigned char* meta = smem + t5_off_meta(NC) + s * 1024;
         const int* hdr = reinterpret_cast<const int*>(meta + T5_META_HDR);
         const unsigned int flags = (unsigned int)hdr[T5_H_FLAGS], tmask = (unsigned int)hdr[T5_H_MASK];
@@ -810,7 +844,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
                 computed |= want; live |= want;
             }
         }
-        if (first_of_block) { T5_STAMP(3 + 5 * blk); first_of_block = false; }
+        if (first_of_block) { T5_STAMP(3 + 5 * blk); t5_trace_tile_end(st, blk, 0, true); first_of_block = false; }
         const unsigned int slotnb = reinterpret_cast<const unsigned short*>(meta + T5_META_SLOTNB)[row];
         const bool valid = slotnb != 0xFFFFu;
         const int slot = valid ? (int)(slotnb >> 8) : 0, nb = (int)(slotnb & 255u);
@@ -820,6 +854,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         t5_wait(bar0 + 8u * (T5_B_SFULL + d), (t >> 1) & 1u);
         t5_fence_after();
         T5_STAMP(tslot);
+        T5_WT(1);
         if (!empty) {
             const unsigned int ta = tmem + lane_base + T5_COL_D1 + 128u * d + (unsigned int)col0;
             t5_ld16(ta, E);
@@ -831,6 +866,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         __syncwarp();
         if (lane == 0) t5_arrive(bar0 + 8u * (T5_B_SFREE + d));
         T5_STAMP(tslot + 1);
+        T5_WT(2);
         if (!empty) {
             // ---- S = exp(-dist / sigma) (harmony.py:466-467) times the penalty (harmony.py:500)
             float ss = 0.f, sp = 0.f, sd = 0.f, se = 0.f, sg = 0.f;
@@ -900,9 +936,11 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
             // ---- the four threads of a cell meet: sums over all clusters
             float2* xs = xch + (t & 1u) * 512;
             T5_STAMP(tslot + 2);
+            T5_WT(3);
             xs[q * 128 + row] = make_float2(ss, sp);
             t5_bar_sync(2 + rq, 128);
             T5_STAMP(tslot + 3);
+            T5_WT(4);
             float sst = 0.f, spt = 0.f;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) { const float2 u = xs[qq * 128 + row]; sst += u.x; spt += u.y; }
@@ -917,6 +955,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
             // ---- operand tiles of the accumulation: wait until the previous tile's MMAs have read them
             if (t > 0 && !waited_acc) t5_wait(bar0 + 8u * (T5_B_ACC + (t - 1u) % T5_NZ), ((t - 1u) / T5_NZ) & 1u);
             T5_STAMP(tslot + 4);
+            T5_WT(5);
             const float sc1024 = sc * HMY_OPSCALE;
             unsigned char* Rh = smem + T5_OFF_RH + (row >> 3) * T5_R_LBO + (row & 7) * 16;
             float* Rg = st.R + (size_t)cell * st.Kp;
@@ -958,6 +997,7 @@ __device__ void t5_epilogue(const HmyDev& st, int mode, unsigned char* smem, uns
         __syncwarp();
         if (lane == 0) t5_arrive(bar0 + 8u * T5_B_RFULL);
         T5_STAMP(tslot + 5);
+        t5_trace_tile_end(st, blk, tile_in_block, false);
         ++t; ++tile_in_block;
         if (flags & T5_F_LAST_BLOCK) {
             T5_STAMP(4 + 5 * blk);
@@ -1159,6 +1199,8 @@ __global__ void __launch_bounds__(T5_THREADS, 1) k_round_tc5(HmyDev st, int mode
     t5_fence_after();
     const unsigned int tmem = *s_tmem;
     hmy_trace(st, 0);
+    if (st.trace != nullptr && lane == 0 && (warp == T5_WARP_PROD || warp == T5_WARP_MMA))       // gaps do not span launches
+        st.trace[(size_t)blockIdx.x * HMY_TRACE_SLOTS + (warp == T5_WARP_PROD ? 184 : 192)] = 0ull;
     if (warp == T5_WARP_PROD) t5_producer<NC>(st, mode, smem, bar0, G);
     else if (warp == T5_WARP_MMA) t5_mma_warp<NC>(st, smem, bar0, tmem);
     else t5_epilogue<NC, MULTI>(st, mode, smem, bar0, tmem, G, bar_base);

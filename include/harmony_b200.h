@@ -47,7 +47,7 @@ enum hmy_matrix {
     HMY_O      = 5, /* double K x B         harmony.py:314-316 */
     HMY_E      = 6, /* double K x B         harmony.py:319-321 */
     HMY_W      = 7, /* float  B x K x d  ridge coefficients of the last hmy_ridge_correct */
-    HMY_TRACE  = 9  /* uint64 (grid + 1) x 192 timeline stamps of the last round kernel (option "trace") */
+    HMY_TRACE  = 9  /* uint64 (grid + 1) x 256 timeline stamps of the last round kernel (option "trace") */
 };
 
 /* Optional caller-supplied sum-all-reduce over ranks, called at the reduction points of the

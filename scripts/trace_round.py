@@ -24,7 +24,7 @@ for _ in range(3):
 eng.set_option("trace", 1)
 ho.kmeans_round()
 G = eng.counter("grid")
-buf = np.zeros((G + 1, 192), dtype=np.uint64)
+buf = np.zeros((G + 1, 256), dtype=np.uint64)
 eng._ck(eng.lib.hmy_get(eng.h, 9, buf.ctypes.data_as(C.c_void_p), buf.nbytes), "trace")
 ser = buf[G].astype(np.int64).reshape(32, 4)
 t = buf[:G].astype(np.int64)

@@ -24,9 +24,10 @@ eng.set_option("write_r", int(os.environ.get("WRITE_R", "0")))
 for _ in range(3):
     ho.kmeans_round()
 eng.set_option("trace", 1)
-ho.kmeans_round()
+for _ in range(int(os.environ.get("TRACE_ROUNDS", "1"))):
+    ho.kmeans_round()
 G = eng.counter("grid")
-buf = np.zeros((G + 1, 192), dtype=np.uint64)
+buf = np.zeros((G + 1, 256), dtype=np.uint64)
 eng._ck(eng.lib.hmy_get(eng.h, 9, buf.ctypes.data_as(C.c_void_p), buf.nbytes), "trace")
 t = buf[:G].astype(np.int64)
 t0 = t[:, 0].min()
@@ -84,3 +85,18 @@ m = cy[:, 0] > 0
 if m.sum():
     d = np.diff(cy[m], axis=1).mean(axis=0)
     print("MMA warp, accumulation of block 5 tile 0, SM cycles: header reads %.0f | slot-sum MMAs %.0f | (o-done commit) | centroid MMAs %.0f | commit %.0f | one globaltimer stamp %.0f" % (d[0], d[1], d[2], d[3], d[4]))
+
+# ---- the slowest tile of every CTA over all traced launches (slots 166..183), and the longest gaps of the producer / MMA warp
+gap = t[:, 174] / 1e3
+order = np.argsort(-gap)
+print("slowest tile per CTA (us): min %.2f  p50 %.2f  p90 %.2f  max %.2f" % (gap.min(), np.median(gap), np.percentile(gap, 90), gap.max()))
+print("CTA  blk tile   gap | after the previous tile's end: described  scores ready  in regs  pass 1  sums met  operand free  end")
+for c in order[:12]:
+    prev = t[c, 183]
+    rel = [(t[c, 176 + i] - prev) / 1e3 for i in range(6)] + [(t[c, 182] - prev) / 1e3]
+    print("%3d  %3d %4d %6.2f | " % (c, t[c, 175] >> 8, t[c, 175] & 255, gap[c]) + "  ".join("%8.2f" % x for x in rel))
+for name, base, n, sites in (("producer", 184, 3, ["stage free", "described", "copies issued"]), ("MMA warp", 192, 4, ["score issue", "score commit", "acc issue", "acc commit"])):
+    for i, sn in enumerate(sites):
+        g = t[:, base + 1 + i] / 1e3
+        c = int(np.argmax(g))
+        print(f"{name}: longest gap ending at '{sn}': p50 {np.median(g):.2f}  p99 {np.percentile(g, 99):.2f}  max {g.max():.2f} us (CTA {c}, tag {int(t[c, base + 1 + n + i])})")
