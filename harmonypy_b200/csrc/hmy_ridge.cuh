@@ -14,7 +14,7 @@
 #include <cuda_fp16.h>
 #include "hmy_common.cuh"
 
-#define HMY_SEG_MAX 1024
+#define HMY_SEG_MAX 256
 
 struct RidgeSmem { int ZS, RS, WS; int off_Zs, off_Rs, off_Wc, total; };
 

@@ -63,6 +63,23 @@ __device__ __forceinline__ void ridge_tile_to_half(const float* src, int ld4, in
     }
 }
 
+// The two passes work tile by tile (load, split, multiply): nothing of a CTA's next tile is in flight while it multiplies.
+// Asking L2 for the NEXT work item's rows (<= HMY_SEG_MAX of R and of Z_orig, contiguous) when an item starts keeps HBM
+// busy during those phases and turns the next tiles' loads into L2 hits.  One bulk prefetch per HMY_MT rows, issued by
+// the first threads of the CTA; addresses and sizes are multiples of 16 bytes (rows are whole float4s).
+__device__ __forceinline__ void ridge_prefetch_item(const HmyDev& st, int it, int i1) {
+    if (it >= i1) return;
+    const long long start = st.seg[3 * it]; const int count = st.seg[3 * it + 1];
+    const int tiles = (count + HMY_MT - 1) / HMY_MT;
+    if ((int)threadIdx.x < 2 * tiles) {
+        const int tl = threadIdx.x >> 1, rows = min(HMY_MT, count - tl * HMY_MT);
+        const float* p; unsigned int bytes;
+        if (threadIdx.x & 1) { p = st.Zorig + (size_t)(start + tl * HMY_MT) * st.dp; bytes = (unsigned int)(rows * st.dp * 4); }
+        else { p = st.R + (size_t)(start + tl * HMY_MT) * st.Kp; bytes = (unsigned int)(rows * st.Kp * 4); }
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+    }
+}
+
 // yacc[i] += (Z tile)^T (R tile) for PC m-tile `mw`, cluster n-tiles [n0, n0 + NT)  (K-dim = cells)
 template <int NT>
 __device__ __forceinline__ void ridge_ztr(float (&yacc)[NT][4], const __half* Zh, const __half* Zl, int ZSH,
@@ -151,8 +168,10 @@ __global__ void __launch_bounds__(128 * WN) k_ridge_moments_mma(HmyDev st, float
     const double inv = 1.0 / ((double)HMY_OPSCALE * (double)zscale);
     int cur = -1;
     const int i0 = (int)((long long)blockIdx.x * st.nseg / gridDim.x), i1 = (int)((long long)(blockIdx.x + 1) * st.nseg / gridDim.x);
+    ridge_prefetch_item(st, i0, i1);
     for (int it = i0; it < i1; ++it) {
         const long long start = st.seg[3 * it]; const int count = st.seg[3 * it + 1], combo = st.seg[3 * it + 2];
+        ridge_prefetch_item(st, it + 1, i1);
         if (combo != cur) { if (cur >= 0 && mw < mtiles) ridge_mma_flush_moments<NT, WN>(st, cur, yacc, mw, n0, inv); cur = combo; }
         for (int tb = 0; tb < count; tb += HMY_MT) {
             const int nt = min(HMY_MT, count - tb);
@@ -207,8 +226,10 @@ __global__ void __launch_bounds__(128 * WN) k_ridge_apply_mma(HmyDev st, const f
     for (int i = 0; i < NT; ++i) yacc[i][0] = yacc[i][1] = yacc[i][2] = yacc[i][3] = 0.f;
     int cur = -1;
     const int i0 = (int)((long long)blockIdx.x * st.nseg / gridDim.x), i1 = (int)((long long)(blockIdx.x + 1) * st.nseg / gridDim.x);
+    ridge_prefetch_item(st, i0, i1);
     for (int it = i0; it < i1; ++it) {
         const long long start = st.seg[3 * it]; const int count = st.seg[3 * it + 1], combo = st.seg[3 * it + 2];
+        ridge_prefetch_item(st, it + 1, i1);
         if (combo != cur) {
             // Wc^T[j][k] = sum_v W[level_v][k][j]: what W.T @ Phi_Rk selects for this combination
             __syncthreads();
