@@ -11,5 +11,5 @@ print('value %.1f M cells/s  ms/step %.2f  round %.3f ms frac %.3f  ridge %.3f m
 print('parity', {k:(v['vs_reference_fp32'], v['kmeans_rounds_equal']) for k,v in d['parity'].items() if isinstance(v,dict)})
 PY
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-parity > gpurun_out/ncu_launches.log 2>&1; echo "launch list exit $?"
-WRITE_R=0 timeout 300 python scripts/trace_tc5.py syn1m > gpurun_out/trace_tc5_w0.txt 2>&1; echo "trace exit $?"
+WRITE_R=0 TRACE_ROUNDS=12 timeout 300 python scripts/trace_tc5.py syn1m > gpurun_out/trace_tc5_w0.txt 2>&1; echo "trace exit $?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_round_tc5 -s 3 -c 1 -o gpurun_out/prof_tc5 python scripts/trace_tc5.py syn1m > gpurun_out/ncu_tc5.log 2>&1; echo "ncu exit $?"
