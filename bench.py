@@ -449,17 +449,31 @@ def run_ours(args, w):
     e2e = None
     if not args.no_e2e:
         from harmonypy_b200.harmony import Harmony as H
+        from harmonypy_b200 import pinned_empty
+        # the caller's inputs live in page-locked host memory (the contract's "from pinned host memory"): the upload
+        # is one DMA; the result comes back in a page-locked buffer of the wrapper's pool, re-used once the previous
+        # result has been dropped (first call: allocation + pinning inside the timed region)
+        Zp = pinned_empty(Z.shape, Z.dtype, local_rank); Zp[...] = Z
+        codes_p = pinned_empty(codes.shape, codes.dtype, local_rank); codes_p[...] = codes
+        prob_p = make_problem(w, Zp, codes_p, Pr_b, N_total, lo)
         times = []
-        for i in range(2):
+        out = None
+        for i in range(3):
+            out = None                       # a caller that loops drops the previous result before the next call
             barrier()
             t0 = time.perf_counter()
-            h2 = H(prob, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, SEED, local_rank, perm_mode="device", comm=comm,
+            h2 = H(prob_p, 0.2, 10, 20, 1e-5, 1e-4, 0.05, False, SEED, local_rank, perm_mode="device", comm=comm,
                    engine_options=opts, init_centroids=Y0, run=True)
             out = h2.result_local()
             barrier()
             times.append(time.perf_counter() - t0)
+            h2_dma = h2._engine.counter("dma_direct")
             del h2
         t_e2e = min(times)
+        # the end-to-end result against the device-resident run timed above (same data, seed and centroids)
+        ref = ho.result_local()
+        e2e_diff = float(np.max(np.abs(out - ref)) / max(float(np.max(np.abs(ref))), 1e-30))
+        del ref
         if dist is not None:
             t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -468,7 +482,10 @@ def run_ours(args, w):
                "h2d_bytes_per_step": int(Z.nbytes + codes.nbytes + 3 * n_local * 4),
                "d2h_bytes_per_step": int(out.nbytes),
                "note": "Harmony(problem, ..., init_centroids) on host arrays: H2D upload, layout sort, "
-                       "init assignment, harmonize to convergence, D2H of Z_corr; best of 2"}
+                       "init assignment, harmonize to convergence, D2H of Z_corr; inputs in page-locked host memory "
+                       "(harmonypy_b200.pinned_empty), result in a pooled page-locked buffer; best of 3",
+               "seconds_all": [float(x) for x in times], "max_rel_diff_vs_resident_run": e2e_diff,
+               "dma_direct": int(h2_dma)}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None

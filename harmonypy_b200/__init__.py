@@ -10,6 +10,9 @@ def __getattr__(name):
     if name in ("run_harmony", "Harmony"):
         from . import harmony
         return getattr(harmony, name)
+    if name == "pinned_empty":            # page-locked host arrays: inputs / results that move with one DMA
+        from ._cabi import pinned_empty
+        return pinned_empty
     if name == "compute_lisi":
         from .lisi import compute_lisi
         return compute_lisi

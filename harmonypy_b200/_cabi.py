@@ -33,6 +33,8 @@ SYMBOLS = {
     "hmy_kmeans_round": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]),
     "hmy_queue_perm": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmy_objectives": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "hmy_host_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),
+    "hmy_host_free": (None, [C.c_void_p]),
     "hmy_ridge_correct": (C.c_int, [C.c_void_p]),
     "hmy_get": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int64]),
     "hmy_synchronize": (C.c_int, [C.c_void_p]),
@@ -74,18 +76,50 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _pinned_alloc(device, nbytes):
+    """Address of `nbytes` of page-locked host memory, or None (no GPU / allocation refused)."""
+    p = load().hmy_host_alloc(int(device), int(nbytes))
+    return int(p) if p else None
+
+
+def _pinned_free(ptr):
+    load().hmy_host_free(C.c_void_p(ptr))
+
+
+def _wrap_address(ptr, nbytes):
+    """uint8 array over foreign memory; views taken from it keep it alive through their `base`."""
+    return np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(ptr))
+
+
+def pinned_empty(shape, dtype=np.float32, device=0):
+    """An uninitialised array in page-locked host memory (hmy_host_alloc): hmy_set_data / hmy_get move such arrays with
+    one DMA instead of staging them through bounce buffers.  The memory is released when the last view of it dies.
+    Falls back to np.empty when page-locked memory is not available."""
+    import weakref
+    shape = tuple(int(x) for x in np.atleast_1d(shape))
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = _pinned_alloc(device, nbytes) if nbytes else None
+    if ptr is None:
+        return np.empty(shape, dtype=dtype)
+    raw = (C.c_ubyte * nbytes).from_address(ptr)
+    weakref.finalize(raw, _pinned_free, ptr)              # every view's base chain ends at `raw`
+    return np.ctypeslib.as_array(raw).view(dtype).reshape(shape)
+
+
 class _ResultPool:
     """Host buffers for the large result reads (Z_corr, R ...).  A fresh NumPy array costs one page fault per 4 KB on
     its first write -- measured: 20-40 ms of a 200 MB read-back -- so buffers whose arrays have been dropped are handed
-    out again.  A buffer is free when nothing but the pool refers to it (the arrays returned to callers are views whose
-    `base` is the buffer, so it cannot be reused while any of them -- or a slice of them -- is alive)."""
+    out again; they are page-locked when the runtime grants it, so that hmy_get fills them with one DMA (no bounce
+    buffer, no host copy).  A buffer is free when nothing but the pool refers to it (the arrays returned to callers
+    are views whose `base` is the buffer, so it cannot be reused while any of them -- or a slice of them -- is alive).
+    Pool buffers live as long as the process (at most MAX_PER_SIZE per size)."""
     MAX_PER_SIZE = 3
     MIN_BYTES = 8 << 20
 
     def __init__(self):
         self._bufs = {}
 
-    def array(self, shape, dtype):
+    def array(self, shape, dtype, device=0):
         import sys
         nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
         if nbytes < self.MIN_BYTES:
@@ -97,9 +131,12 @@ class _ResultPool:
                 owner = b
                 break
         if owner is None:
-            owner = np.empty(nbytes, dtype=np.uint8)
             if len(lst) < self.MAX_PER_SIZE:
+                ptr = _pinned_alloc(device, nbytes)
+                owner = _wrap_address(ptr, nbytes) if ptr is not None else np.empty(nbytes, dtype=np.uint8)
                 lst.append(owner)
+            else:
+                owner = np.empty(nbytes, dtype=np.uint8)
         return owner.view(dtype).reshape(shape)
 
 
@@ -111,6 +148,7 @@ class Engine:
 
     def __init__(self, device, n_local, n_global, cell_offset, d, K, levels_per_var):
         self.lib = load()
+        self.device = int(device)
         self.n_local, self.n_global, self.cell_offset = int(n_local), int(n_global), int(cell_offset)
         self.d, self.K = int(d), int(K)
         self.levels = np.ascontiguousarray(levels_per_var, dtype=np.int32)
@@ -221,7 +259,7 @@ class Engine:
             R: ((n, K), np.float32), Y: ((K, d), np.float32), O: ((K, B), np.float64), E: ((K, B), np.float64),
             W: ((B, K, d), np.float32),
         }[which]
-        out = _POOL.array(shape, dt)
+        out = _POOL.array(shape, dt, self.device)
         self._ck(self.lib.hmy_get(self.h, int(which), _ptr(out), out.nbytes), "hmy_get")
         return out
 

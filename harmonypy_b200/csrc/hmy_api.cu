@@ -62,6 +62,7 @@ struct hmy_ctx {
     unsigned long long bar_count64 = 0;     // host mirror of the device grid-barrier counter
     long long n_assigned = 0, n_done = 0;   // rounds (since init) with a block assignment / executed
     int write_r = 1; bool r_valid = true;   // R rows in HBM are those of the last stage
+    long long dma_direct = 0;               // transfers that went straight from / to the caller's page-locked array
     double* objring = nullptr;              // [16][4] objective sums of the last stages (tc5 path), [16][2] all-rank sums behind them
     long long stages_launched = 0;          // tc5 stages launched so far (ring slot = stages_launched % 16)
     int G = 0, sms = 0;
@@ -479,10 +480,35 @@ static int ensure_stage(hmy_ctx* ctx) {
     return 0;
 }
 
+// true when p lies in page-locked host memory the CUDA runtime knows (hmy_host_alloc, cudaHostAlloc, cudaHostRegister,
+// torch pinned tensors): such arrays move by DMA alone
+static bool host_is_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" void* hmy_host_alloc(int device, size_t bytes) {
+    void* p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void hmy_host_free(void* p) {
+    if (p && cudaFreeHost(p) != cudaSuccess) (void)cudaGetLastError();
+}
+
 // pageable host memory -> device through the two pinned bounce buffers: the host copy of chunk i + 1 (spread over
 // threads) overlaps the DMA of chunk i (a plain cudaMemcpy from pageable memory stages single-threaded inside the driver)
 static int h2d_staged(hmy_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
     constexpr size_t CHUNK = HMY_STAGE_CHUNK;
+    if (bytes >= (1u << 20) && host_is_pinned(src_host)) {
+        // the caller keeps the array in page-locked memory: one DMA, no host copy (every caller of this function
+        // synchronises the stream before the source can go away)
+        CK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->dma_direct++;
+        return 0;
+    }
     if (ensure_stage(ctx)) return 1;
     const unsigned char* src8 = (const unsigned char*)src_host; unsigned char* dst8 = (unsigned char*)dst_dev;
     const size_t nchunk = (bytes + CHUNK - 1) / CHUNK;
@@ -1083,6 +1109,12 @@ static int get_cells(hmy_ctx* ctx, const float* src, int sp, int w, void* host_o
     k_unsort_rows<<<(unsigned int)((threads + 255) / 256), 256, 0, ctx->stream>>>(src, sp, ctx->d_tmp, w, st.order, st.N);
     ctx->launches++;
     CK(cudaGetLastError());
+    if (need >= (1u << 20) && host_is_pinned(host_out)) {       // page-locked destination: one DMA, no bounce, no host copy
+        CK(cudaMemcpyAsync(host_out, ctx->d_tmp, need, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->dma_direct++;
+        return 0;
+    }
     // device -> pinned bounce buffer -> caller's (pageable, usually untouched) array, double buffered:
     // the DMA of chunk i+1 overlaps the host copy (and first-touch page faults) of chunk i
     constexpr size_t CHUNK = HMY_STAGE_CHUNK;
@@ -1247,6 +1279,7 @@ extern "C" int64_t hmy_counter(const hmy_ctx* ctx, const char* name) {
     if (n == "ridge_mma") return ctx->ridge_mma ? 1 : 0;
     if (n == "round_threads") return use_tc5(ctx) ? T5_THREADS : ctx->round_threads;
     if (n == "tc5") return use_tc5(ctx) ? 1 : 0;
+    if (n == "dma_direct") return ctx->dma_direct;
     if (n == "lookahead") return use_tc5(ctx) ? 1 : 0;      // 1: permutations are queued one round ahead (hmy_queue_perm)
     if (n == "r_valid") return ctx->r_valid ? 1 : 0;
     return -1;

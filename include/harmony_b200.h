@@ -29,6 +29,7 @@
 #ifndef HARMONY_B200_H
 #define HARMONY_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -57,6 +58,13 @@ typedef int (*hmy_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int dt
 
 const char* hmy_version(void);
 const char* hmy_last_error(const hmy_ctx* ctx);
+
+/* Page-locked ("pinned") host memory, usable from every device of the process.  hmy_set_data and hmy_get recognise
+ * arrays that live in page-locked memory (from here, cudaHostAlloc / cudaHostRegister, torch pinned tensors) and move
+ * them with ONE DMA; pageable arrays are staged through the context's two pinned 16 MB buffers by a few host threads.
+ * hmy_host_alloc returns NULL on failure (no GPU, out of lockable memory); hmy_host_free(NULL) is a no-op. */
+void* hmy_host_alloc(int device, size_t bytes);
+void  hmy_host_free(void* p);
 
 /* State owner.  Replaces Harmony.__init__ buffers + allocate_buffers (harmony.py:224-271,
  * :357-364).  n_local cells live on this rank; they are cells [cell_offset, cell_offset +
@@ -136,7 +144,7 @@ int hmy_synchronize(hmy_ctx* ctx);
  *   "relaxed"    0/1   fused multi-GPU mode: exchange the K x B table once per round instead of once
  *                      per block (NOT exact; default 0)
  *   "dbg"        bits  timing experiments on the tensor-memory round kernel (skips parts of its work: results are WRONG
- *                      when non-zero; default 0; scripts/gpu_dbg.sh)
+ *                      when non-zero; default 0)
  *   "timing"     0/1   CUDA-event timers around the stages (default 1)
  *   "reset"      1     back to the state right after hmy_set_data (benchmark restarts)
  *   "trace"      1     per-CTA timeline of the round kernel, read with hmy_get(HMY_TRACE) */
@@ -144,7 +152,8 @@ int hmy_set_option(hmy_ctx* ctx, const char* name, int64_t value);
 
 /* Counters: "launches" (kernels launched by this library since creation), "rounds",
  * "ridge_passes", "grid", "nblk", "ncombo", "mma", "ridge_mma", "fused", "round_threads",
- * "smem_round", "tc5", "lookahead", "r_valid".  Timers (CUDA events on the context stream, milliseconds, cumulative):
+ * "smem_round", "tc5", "lookahead", "r_valid", "dma_direct" (uploads / read-backs that moved with one DMA because the
+ * caller's array is page-locked).  Timers (CUDA events on the context stream, milliseconds, cumulative):
  * "ms_round", "ms_ridge", "ms_init".  Unknown names return -1. */
 int64_t hmy_counter(const hmy_ctx* ctx, const char* name);
 double hmy_timer_ms(hmy_ctx* ctx, const char* name);

@@ -308,3 +308,33 @@ def test_max_iter_harmony_zero_returns_input():
     ho = run_harmony(Z, meta, ["var0"], nclust=10, max_iter_harmony=0, verbose=False)
     np.testing.assert_array_equal(ho.Z_corr, Z)
     assert len(ho.objective_harmony) == 1 and ho.kmeans_rounds == []
+
+
+def test_page_locked_inputs_and_results_match_pageable_ones():
+    """Arrays in page-locked host memory (harmonypy_b200.pinned_empty, or the wrapper's result pool) move with one
+    DMA instead of the staged copy: same results, and the counter shows which path ran."""
+    from harmonypy_b200 import pinned_empty
+    from harmonypy_b200.harmony import Harmony, Problem
+    from harmonypy_b200.synthetic import make_synthetic_arrays
+    N, d, K, levels = 120000, 20, 30, [6]
+    Z, codes = make_synthetic_arrays(N, d, levels, seed=3)
+    Y0 = Z[np.random.default_rng(1).choice(N, K, replace=False)]
+    Pr_b = (np.bincount(codes[0], minlength=6) / N).astype(np.float32)
+
+    def run(Zin, cin):
+        prob = Problem(Z=Zin, codes=cin, levels=np.asarray(levels, np.int32), level_names=[], Pr_b=Pr_b,
+                       theta=np.full(6, 2, np.float32), lamb=np.concatenate([[0], np.ones(6)]).astype(np.float32),
+                       lambda_estimation=False, sigma=np.full(K, 0.1, np.float32), K=K)
+        ho = Harmony(prob, 0.2, 2, 6, 1e-5, 1e-4, 0.05, False, 7, 0, init_centroids=Y0, run=True)
+        return ho, ho.Z_corr, ho.R, ho._engine.counter("dma_direct")
+
+    ho_a, Za, Ra, dma_a = run(Z, codes)
+    Zp = pinned_empty(Z.shape, np.float32); Zp[...] = Z
+    cp = pinned_empty(codes.shape, codes.dtype); cp[...] = codes
+    assert not Zp.flags.owndata, "page-locked memory was refused on a GPU box"
+    ho_b, Zb, Rb, dma_b = run(Zp, cp)
+    # Z_corr (9.6 MB) and R (14.4 MB) come back in pooled page-locked buffers in both runs; only run b uploads from one
+    assert dma_a >= 2 and dma_b == dma_a + 1, (dma_a, dma_b)
+    assert list(ho_a.kmeans_rounds) == list(ho_b.kmeans_rounds)
+    assert rel_max(Zb, Za) < 1e-5 and rel_max(Rb, Ra) < 1e-4
+    np.testing.assert_array_equal(ho_b._engine.get(2), Z)            # Z_ORIG: the upload itself, bit for bit
