@@ -102,7 +102,8 @@ def pinned_empty(shape, dtype=np.float32, device=0):
     if ptr is None:
         return np.empty(shape, dtype=dtype)
     raw = (C.c_ubyte * nbytes).from_address(ptr)
-    weakref.finalize(raw, _pinned_free, ptr)              # every view's base chain ends at `raw`
+    fin = weakref.finalize(raw, _pinned_free, ptr)        # every view's base chain ends at `raw`
+    fin.atexit = False                                    # at interpreter exit the process's memory goes anyway: no CUDA calls during teardown
     return np.ctypeslib.as_array(raw).view(dtype).reshape(shape)
 
 
