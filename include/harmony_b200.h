@@ -111,7 +111,8 @@ int hmy_kmeans_round(hmy_ctx* ctx, const int64_t* perm_host, double obj[3]);
  * sums of the last n stages (oldest first, 3 doubles each, n <= 16).  With "lookahead" = 0 obj must not be NULL. */
 int hmy_objectives(hmy_ctx* ctx, int n, double* obj_3n);
 
-/* Contexts whose counter "lookahead" is 1 (single-GPU persistent runs on the tensor-memory round kernel) run the
+/* Contexts whose counter "lookahead" is 1 (the tensor-memory round kernel: one GPU, or several with the peer exchange
+ * of hmy_comm_attach) run the
  * block permutations ONE ROUND AHEAD: a round already accumulates, per block of the NEXT round, the sums that round
  * will remove from O (harmony.py:491-492), so it must know the next round's blocks.  Call order there:
  *     hmy_queue_perm(perm of round 0)            (omit with device-side permutations)
